@@ -1,0 +1,181 @@
+// Shared host/device helpers for libfastdm_b200.so (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/fastdm_b200.h"
+
+namespace fdm {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+int require_sm100();   // FDM_OK or FDM_ERR_ARCH for the current device
+int num_sms();         // SM count of the current device (cached)
+
+#define FDM_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      ::fdm::set_error(__VA_ARGS__);           \
+      return FDM_ERR_ARG;                      \
+    }                                          \
+  } while (0)
+
+#define FDM_CUDA(call)                                         \
+  do {                                                         \
+    cudaError_t e__ = (call);                                  \
+    if (e__ != cudaSuccess) return ::fdm::cuda_fail(e__, #call); \
+  } while (0)
+
+#define FDM_LAUNCH_CHECK(name)                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return ::fdm::cuda_fail(e__, name);  \
+  } while (0)
+
+// ---- 16-byte vector of raw bits ---------------------------------------------------------------
+struct alignas(16) U128 {
+  uint32_t x, y, z, w;
+};
+
+__device__ __forceinline__ U128 ldg128_stream(const void* p) {
+  U128 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ U128 ldg128(const void* p) {
+  return *reinterpret_cast<const U128*>(p);
+}
+__device__ __forceinline__ void stg128(void* p, const U128& v) {
+  *reinterpret_cast<U128*>(p) = v;
+}
+__device__ __forceinline__ void stg64(void* p, uint32_t a, uint32_t b) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(a, b);
+}
+
+// ---- dtype traits: load 8 elements as floats ---------------------------------------------------
+template <typename T>
+struct Elem;
+template <>
+struct Elem<__nv_bfloat16> {
+  static constexpr int kId = FDM_BF16;
+  __device__ static __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <>
+struct Elem<__half> {
+  static constexpr int kId = FDM_F16;
+  __device__ static __forceinline__ float to_f(__half v) { return __half2float(v); }
+  __device__ static __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+template <>
+struct Elem<float> {
+  static constexpr int kId = FDM_F32;
+  __device__ static __forceinline__ float to_f(float v) { return v; }
+  __device__ static __forceinline__ float from_f(float v) { return v; }
+};
+
+// bf16 / f16 pair <-> packed 32-bit
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  __half2 t = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float f16lo(uint32_t u) {
+  return __half2float(__ushort_as_half((unsigned short)(u & 0xffff)));
+}
+__device__ __forceinline__ float f16hi(uint32_t u) {
+  return __half2float(__ushort_as_half((unsigned short)(u >> 16)));
+}
+
+template <typename T>
+__device__ __forceinline__ void unpack8(const U128& v, float (&f)[8]);
+template <>
+__device__ __forceinline__ void unpack8<__nv_bfloat16>(const U128& v, float (&f)[8]) {
+  f[0] = bf16lo(v.x); f[1] = bf16hi(v.x); f[2] = bf16lo(v.y); f[3] = bf16hi(v.y);
+  f[4] = bf16lo(v.z); f[5] = bf16hi(v.z); f[6] = bf16lo(v.w); f[7] = bf16hi(v.w);
+}
+template <>
+__device__ __forceinline__ void unpack8<__half>(const U128& v, float (&f)[8]) {
+  f[0] = f16lo(v.x); f[1] = f16hi(v.x); f[2] = f16lo(v.y); f[3] = f16hi(v.y);
+  f[4] = f16lo(v.z); f[5] = f16hi(v.z); f[6] = f16lo(v.w); f[7] = f16hi(v.w);
+}
+template <typename T>
+__device__ __forceinline__ U128 pack8(const float (&f)[8]);
+template <>
+__device__ __forceinline__ U128 pack8<__nv_bfloat16>(const float (&f)[8]) {
+  U128 r;
+  r.x = pack_bf16(f[0], f[1]); r.y = pack_bf16(f[2], f[3]);
+  r.z = pack_bf16(f[4], f[5]); r.w = pack_bf16(f[6], f[7]);
+  return r;
+}
+template <>
+__device__ __forceinline__ U128 pack8<__half>(const float (&f)[8]) {
+  U128 r;
+  r.x = pack_f16(f[0], f[1]); r.y = pack_f16(f[2], f[3]);
+  r.z = pack_f16(f[4], f[5]); r.w = pack_f16(f[6], f[7]);
+  return r;
+}
+
+// round-trip a float through T (the "rounded to the tensor dtype" step of the torch oracle)
+template <typename T>
+__device__ __forceinline__ float round_to(float v) {
+  return Elem<T>::to_f(Elem<T>::from_f(v));
+}
+
+// ---- fp8 e4m3 conversion: two floats -> two e4m3 bytes (RNE, saturate-to-finite) ---------------
+__device__ __forceinline__ uint16_t cvt_e4m3x2(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t cvt_e4m3x4(float a, float b, float c, float d) {
+  return (uint32_t)cvt_e4m3x2(a, b) | ((uint32_t)cvt_e4m3x2(c, d) << 16);
+}
+
+// ---- reductions --------------------------------------------------------------------------------
+template <int W = 32>
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int W = 32>
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int W = 32>
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- activations (fp32 in / fp32 out; callers round to the tensor dtype) ------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  // ATen: inner = sqrt(2/pi) * (x + 0.044715 * x^3); 0.5 * x * (1 + tanh(inner))
+  const float kBeta = 0.79788456080286535588f;
+  const float kKappa = 0.044715f;
+  float x3 = x * x * x;
+  float inner = kBeta * (x + kKappa * x3);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+
+}  // namespace fdm

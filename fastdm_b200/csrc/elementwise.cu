@@ -1,0 +1,779 @@
+// Family 3: HBM-bound ops of the DiT block -- per-token FP8 / INT8 dynamic quantisation (optionally
+// fused with the preceding GELU), RMSNorm, RoPE, GELU-and-mul.
+//
+// Design (B200): every kernel makes exactly one pass over HBM -- the row (or row group) is pulled
+// into registers with 128-bit coalesced loads, reduced with warp shuffles (+ one shared-memory hop
+// for multi-warp rows), transformed in registers and written back with 64/128-bit stores.
+// The reference kernels (csrc/elmwise_ops.cu) read each row twice, use 8-byte loads and one CTA
+// per (token, head); arithmetic here follows the *torch backend* (fastdm/kernel/torch/*.py), which
+// is the parity oracle, not the reference CUDA formulas (SURVEY.md finding 0.6).
+#include "common.cuh"
+
+namespace fdm {
+
+// ------------------------------------------------------------------------------------------------
+// block-wide min/max/sum helpers (blockDim.x <= 1024, multiple of 32)
+// ------------------------------------------------------------------------------------------------
+struct MinMax {
+  float mn, mx;
+};
+
+__device__ __forceinline__ MinMax block_minmax(float mn, float mx, float* smem /*>=64 floats*/) {
+  mn = warp_min(mn);
+  mx = warp_max(mx);
+  const int nw = blockDim.x >> 5;
+  if (nw == 1) return {mn, mx};
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    smem[w] = mn;
+    smem[32 + w] = mx;
+  }
+  __syncthreads();
+  float a = (l < nw) ? smem[l] : INFINITY;
+  float b = (l < nw) ? smem[32 + l] : -INFINITY;
+  a = warp_min(a);
+  b = warp_max(b);
+  __syncthreads();  // smem reusable by the caller afterwards
+  return {a, b};
+}
+
+__device__ __forceinline__ float block_sum(float v, float* smem /*>=32 floats*/) {
+  v = warp_sum(v);
+  const int nw = blockDim.x >> 5;
+  if (nw == 1) return v;
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  float a = (l < nw) ? smem[l] : 0.f;
+  a = warp_sum(a);
+  __syncthreads();
+  return a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-token quantisation.  MODE 0: fp8 e4m3 (torch/quantize.py:45-67)
+//                          MODE 1: int8 symmetric (torch/quantize.py:33-36)
+//                          MODE 2: int8 asymmetric (torch/quantize.py:38-41)
+// ACT: FDM_ACT_* applied (and rounded to T) before quantisation.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float fp8_amax_floor();
+// torch: abs_max.clamp(min=1e-12) evaluated in the tensor dtype
+template <>
+__device__ __forceinline__ float fp8_amax_floor<__nv_bfloat16>() {
+  return round_to<__nv_bfloat16>(1e-12f);
+}
+template <>
+__device__ __forceinline__ float fp8_amax_floor<__half>() {
+  return round_to<__half>(1e-12f);  // == 0 in fp16, as in torch
+}
+template <>
+__device__ __forceinline__ float fp8_amax_floor<float>() {
+  return 1e-12f;
+}
+
+template <int ACT, typename T>
+__device__ __forceinline__ float apply_act(float x) {
+  if (ACT == FDM_ACT_GELU_TANH) return round_to<T>(gelu_tanh(x));
+  if (ACT == FDM_ACT_GELU_ERF) return round_to<T>(gelu_erf(x));
+  return x;
+}
+
+struct QParams {
+  float scale;  // per-row scale
+  float zpf;    // float(zero point) (MODE 2)
+  int zp;
+};
+
+template <int MODE>
+__device__ __forceinline__ QParams make_qparams(float mn, float mx, float amax_floor) {
+  QParams p;
+  p.zpf = 0.f;
+  p.zp = 0;
+  if (MODE == 0) {
+    float amax = fmaxf(fmaxf(fabsf(mn), fabsf(mx)), amax_floor);
+    p.scale = __fdiv_rn(amax, 448.0f);
+  } else if (MODE == 1) {
+    float amax = fmaxf(fabsf(mn), fabsf(mx));
+    p.scale = __fdiv_rn(amax, 127.0f);
+  } else {
+    p.scale = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+    p.zpf = __fsub_rn(-128.0f, rintf(__fdiv_rn(mn, p.scale)));
+    p.zp = (int)p.zpf;
+    p.zpf = (float)p.zp;
+  }
+  return p;
+}
+
+template <int MODE>
+__device__ __forceinline__ float qtransform(float x, const QParams& p) {
+  float q = __fdiv_rn(x, p.scale);
+  if (MODE == 0) return fminf(fmaxf(q, -448.0f), 448.0f);
+  if (MODE == 2) q = __fadd_rn(q, p.zpf);
+  q = rintf(q);
+  return fminf(fmaxf(q, -128.0f), 127.0f);
+}
+
+__device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {
+  return (uint32_t)((int)a & 0xff) | ((uint32_t)((int)b & 0xff) << 8) |
+         ((uint32_t)((int)c & 0xff) << 16) | ((uint32_t)((int)d & 0xff) << 24);
+}
+
+// One CTA per row, the row lives in registers: VPT 16-byte vectors per thread.
+template <typename T, int MODE, int ACT, int VPT>
+__global__ void __launch_bounds__(256) quant_row_kernel(const T* __restrict__ in,
+                                                        uint8_t* __restrict__ out,
+                                                        float* __restrict__ scale,
+                                                        int32_t* __restrict__ azp, int cols,
+                                                        int64_t in_row_stride) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  const int nvec = cols >> 3;
+  const T* src = in + row * in_row_stride;
+  float f[VPT][8];
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      U128 raw = ldg128_stream(src + (int64_t)v * 8);
+      unpack8<T>(raw, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[i][j] = apply_act<ACT, T>(f[i][j]);
+        mn = fminf(mn, f[i][j]);
+        mx = fmaxf(mx, f[i][j]);
+      }
+    }
+  }
+  MinMax r = block_minmax(mn, mx, red);
+  const QParams p = make_qparams<MODE>(r.mn, r.mx, fp8_amax_floor<T>());
+  if (threadIdx.x == 0) {
+    scale[row] = p.scale;
+    if (MODE == 2) azp[row] = p.zp;
+  }
+  uint8_t* dst = out + row * (int64_t)cols;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = qtransform<MODE>(f[i][j], p);
+      uint32_t lo, hi;
+      if (MODE == 0) {
+        lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
+        hi = cvt_e4m3x4(q[4], q[5], q[6], q[7]);
+      } else {
+        lo = pack_s8x4(q[0], q[1], q[2], q[3]);
+        hi = pack_s8x4(q[4], q[5], q[6], q[7]);
+      }
+      stg64(dst + (int64_t)v * 8, lo, hi);
+    }
+  }
+}
+
+// Generic fallback (any cols / alignment / fp32 input): one CTA per row, the row is re-read from L2.
+template <typename T, int MODE, int ACT>
+__global__ void __launch_bounds__(256) quant_row_generic_kernel(const T* __restrict__ in,
+                                                                uint8_t* __restrict__ out,
+                                                                float* __restrict__ scale,
+                                                                int32_t* __restrict__ azp,
+                                                                int64_t cols,
+                                                                int64_t in_row_stride) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  const T* src = in + row * in_row_stride;
+  float mn = INFINITY, mx = -INFINITY;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+    float x = apply_act<ACT, T>(Elem<T>::to_f(src[c]));
+    mn = fminf(mn, x);
+    mx = fmaxf(mx, x);
+  }
+  MinMax r = block_minmax(mn, mx, red);
+  const QParams p = make_qparams<MODE>(r.mn, r.mx, fp8_amax_floor<T>());
+  if (threadIdx.x == 0) {
+    scale[row] = p.scale;
+    if (MODE == 2) azp[row] = p.zp;
+  }
+  uint8_t* dst = out + row * cols;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+    float x = apply_act<ACT, T>(Elem<T>::to_f(src[c]));
+    float q = qtransform<MODE>(x, p);
+    if (MODE == 0) {
+      dst[c] = (uint8_t)(cvt_e4m3x2(q, 0.f) & 0xff);
+    } else {
+      dst[c] = (uint8_t)((int)q & 0xff);
+    }
+  }
+}
+
+template <typename T, int MODE, int ACT>
+static int launch_quant_t(const void* in, void* out, float* scale, int32_t* azp, int64_t rows,
+                          int64_t cols, int64_t stride, cudaStream_t st) {
+  const T* src = (const T*)in;
+  uint8_t* dst = (uint8_t*)out;
+  const bool vec_ok = sizeof(T) == 2 && (cols % 8 == 0) && (stride % 8 == 0) &&
+                      ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 8 == 0) && cols <= 8 * 256 * 8;
+  if (!vec_ok) {
+    quant_row_generic_kernel<T, MODE, ACT><<<(unsigned)rows, 256, 0, st>>>(src, dst, scale, azp,
+                                                                           cols, stride);
+    return FDM_OK;
+  }
+  if constexpr (sizeof(T) == 2) {
+    const int nvec = (int)(cols / 8);
+    int block = ((nvec + 31) / 32) * 32;
+    if (block > 256) block = 256;
+    const int vpt = (nvec + block - 1) / block;
+    const unsigned g = (unsigned)rows;
+    if (vpt <= 1)
+      quant_row_kernel<T, MODE, ACT, 1><<<g, block, 0, st>>>(src, dst, scale, azp, (int)cols, stride);
+    else if (vpt <= 2)
+      quant_row_kernel<T, MODE, ACT, 2><<<g, block, 0, st>>>(src, dst, scale, azp, (int)cols, stride);
+    else if (vpt <= 4)
+      quant_row_kernel<T, MODE, ACT, 4><<<g, block, 0, st>>>(src, dst, scale, azp, (int)cols, stride);
+    else
+      quant_row_kernel<T, MODE, ACT, 8><<<g, block, 0, st>>>(src, dst, scale, azp, (int)cols, stride);
+  }
+  return FDM_OK;
+}
+
+template <int MODE, int ACT>
+static int launch_quant_d(const void* in, void* out, float* scale, int32_t* azp, int64_t rows,
+                          int64_t cols, int64_t stride, int dtype, cudaStream_t st) {
+  switch (dtype) {
+    case FDM_BF16:
+      return launch_quant_t<__nv_bfloat16, MODE, ACT>(in, out, scale, azp, rows, cols, stride, st);
+    case FDM_F16:
+      return launch_quant_t<__half, MODE, ACT>(in, out, scale, azp, rows, cols, stride, st);
+    case FDM_F32:
+      if (ACT == FDM_ACT_NONE)
+        return launch_quant_t<float, MODE, FDM_ACT_NONE>(in, out, scale, azp, rows, cols, stride, st);
+      // fallthrough
+    default:
+      set_error("quant: unsupported input dtype %d", dtype);
+      return FDM_ERR_UNSUPPORTED;
+  }
+}
+
+template <int MODE>
+static int launch_quant(const void* in, void* out, float* scale, int32_t* azp, int64_t rows,
+                        int64_t cols, int64_t stride, int dtype, int act, cudaStream_t st) {
+  switch (act) {
+    case FDM_ACT_NONE:
+      return launch_quant_d<MODE, FDM_ACT_NONE>(in, out, scale, azp, rows, cols, stride, dtype, st);
+    case FDM_ACT_GELU_TANH:
+      return launch_quant_d<MODE, FDM_ACT_GELU_TANH>(in, out, scale, azp, rows, cols, stride, dtype, st);
+    case FDM_ACT_GELU_ERF:
+      return launch_quant_d<MODE, FDM_ACT_GELU_ERF>(in, out, scale, azp, rows, cols, stride, dtype, st);
+    default:
+      set_error("quant: unknown activation %d", act);
+      return FDM_ERR_ARG;
+  }
+}
+
+static int quant_common(const void* in, void* out, float* scale, int32_t* azp, int64_t rows,
+                        int64_t cols, int64_t stride, int dtype, int act, int mode, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(rows >= 0 && cols >= 0, "quant: negative shape");
+  if (rows == 0 || cols == 0) return FDM_OK;
+  FDM_REQUIRE(in && out && scale, "quant: null pointer");
+  FDM_REQUIRE(stride >= cols, "quant: in_row_stride (%lld) < cols (%lld)", (long long)stride,
+              (long long)cols);
+  FDM_REQUIRE(rows <= 0x7fffffffLL, "quant: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0)
+    rc = launch_quant<0>(in, out, scale, nullptr, rows, cols, stride, dtype, act, st);
+  else if (mode == 1)
+    rc = launch_quant<1>(in, out, scale, nullptr, rows, cols, stride, dtype, act, st);
+  else
+    rc = launch_quant<2>(in, out, scale, azp, rows, cols, stride, dtype, act, st);
+  if (rc) return rc;
+  FDM_LAUNCH_CHECK("quant kernel launch");
+  return FDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RMSNorm (torch/norm.py:5-27): y = T( T(x * rsqrt(mean(x^2)+eps)) * w )
+// ------------------------------------------------------------------------------------------------
+// Short rows (cols <= 256, multiple of 8): LANES lanes per row, 32/LANES rows per warp.
+template <typename T, int LANES>
+__global__ void __launch_bounds__(256) rmsnorm_short_kernel(const T* __restrict__ in,
+                                                            T* __restrict__ out,
+                                                            const T* __restrict__ w, int64_t rows,
+                                                            int cols, int64_t in_stride,
+                                                            int64_t out_stride, float eps) {
+  constexpr int RPW = 32 / LANES;  // rows per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LANES;    // which row of the warp's group
+  const int li = lane % LANES;     // lane within the row
+  const bool active = li * 8 < cols;
+  float wv[8];
+  if (w != nullptr && active) {
+    unpack8<T>(ldg128(w + li * 8), wv);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = 1.f;
+  }
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warp_count = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const float inv_cols = 1.0f / (float)cols;
+  constexpr int UNROLL = 4;
+  for (int64_t base = warp_global * RPW; base < rows; base += warp_count * RPW * UNROLL) {
+    U128 raw[UNROLL];
+    int64_t r[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      r[u] = base + (int64_t)u * warp_count * RPW + sub;
+      if (r[u] < rows && active) raw[u] = ldg128_stream(in + r[u] * in_stride + li * 8);
+      else raw[u] = U128{0, 0, 0, 0};
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float f[8];
+      unpack8<T>(raw[u], f);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      ss = warp_sum<LANES>(ss);
+      const float rs = rsqrtf(ss * inv_cols + eps);
+      if (r[u] < rows && active) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float n = round_to<T>(f[j] * rs);
+          o[j] = (w != nullptr) ? n * wv[j] : n;
+        }
+        stg128(out + r[u] * out_stride + li * 8, pack8<T>(o));
+      }
+    }
+  }
+}
+
+// Long rows: one CTA per row, row in registers.
+template <typename T, int VPT>
+__global__ void __launch_bounds__(256) rmsnorm_long_kernel(const T* __restrict__ in,
+                                                           T* __restrict__ out,
+                                                           const T* __restrict__ w, int cols,
+                                                           int64_t in_stride, int64_t out_stride,
+                                                           float eps) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const int nvec = cols >> 3;
+  const T* src = in + row * in_stride;
+  float f[VPT][8];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      unpack8<T>(ldg128_stream(src + (int64_t)v * 8), f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[i][j] * f[i][j];
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rs = rsqrtf(ss / (float)cols + eps);
+  T* dst = out + row * out_stride;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float o[8];
+      if (w != nullptr) {
+        float wv[8];
+        unpack8<T>(ldg128(w + (int64_t)v * 8), wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = round_to<T>(f[i][j] * rs) * wv[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = f[i][j] * rs;
+      }
+      stg128(dst + (int64_t)v * 8, pack8<T>(o));
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_generic_kernel(const T* __restrict__ in,
+                                                              T* __restrict__ out,
+                                                              const T* __restrict__ w,
+                                                              int64_t cols, int64_t in_stride,
+                                                              int64_t out_stride, float eps) {
+  __shared__ float red[32];
+  const int64_t row = blockIdx.x;
+  const T* src = in + row * in_stride;
+  float ss = 0.f;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+    float x = Elem<T>::to_f(src[c]);
+    ss += x * x;
+  }
+  ss = block_sum(ss, red);
+  const float rs = rsqrtf(ss / (float)cols + eps);
+  T* dst = out + row * out_stride;
+  for (int64_t c = threadIdx.x; c < cols; c += blockDim.x) {
+    float x = Elem<T>::to_f(src[c]);
+    float n = x * rs;
+    if (w != nullptr) n = round_to<T>(n) * Elem<T>::to_f(w[c]);
+    dst[c] = Elem<T>::from_f(n);
+  }
+}
+
+template <typename T>
+static int launch_rmsnorm(const void* in, void* out, const void* w, int64_t rows, int64_t cols,
+                          int64_t is, int64_t os, float eps, cudaStream_t st) {
+  const T* src = (const T*)in;
+  T* dst = (T*)out;
+  const T* wt = (const T*)w;
+  const bool vec_ok = (cols % 8 == 0) && (is % 8 == 0) && (os % 8 == 0) &&
+                      ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) &&
+                      (w == nullptr || (uintptr_t)w % 16 == 0) && cols <= 8 * 256 * 8;
+  if (!vec_ok) {
+    rmsnorm_generic_kernel<T><<<(unsigned)rows, 256, 0, st>>>(src, dst, wt, cols, is, os, eps);
+    return FDM_OK;
+  }
+  const int nvec = (int)(cols / 8);
+  if (nvec <= 32) {
+    int lanes = 1;
+    while (lanes < nvec) lanes <<= 1;
+    const int rpw = 32 / lanes;
+    const int64_t warps_needed = (rows + rpw - 1) / rpw;
+    int64_t blocks = (warps_needed + 7) / 8;
+    const int64_t cap = (int64_t)num_sms() * 8;
+    // each warp walks UNROLL row groups per trip: shrink the grid accordingly but keep >= 1 wave
+    int64_t want = (blocks + 3) / 4;
+    if (want < 1) want = 1;
+    if (want > cap * 4) want = cap * 4;
+    const unsigned g = (unsigned)want;
+#define RMS_SHORT(L) \
+  rmsnorm_short_kernel<T, L><<<g, 256, 0, st>>>(src, dst, wt, rows, (int)cols, is, os, eps)
+    switch (lanes) {
+      case 1: RMS_SHORT(1); break;
+      case 2: RMS_SHORT(2); break;
+      case 4: RMS_SHORT(4); break;
+      case 8: RMS_SHORT(8); break;
+      case 16: RMS_SHORT(16); break;
+      default: RMS_SHORT(32); break;
+    }
+#undef RMS_SHORT
+    return FDM_OK;
+  }
+  int block = ((nvec + 31) / 32) * 32;
+  if (block > 256) block = 256;
+  const int vpt = (nvec + block - 1) / block;
+  const unsigned g = (unsigned)rows;
+  if (vpt <= 1)
+    rmsnorm_long_kernel<T, 1><<<g, block, 0, st>>>(src, dst, wt, (int)cols, is, os, eps);
+  else if (vpt <= 2)
+    rmsnorm_long_kernel<T, 2><<<g, block, 0, st>>>(src, dst, wt, (int)cols, is, os, eps);
+  else if (vpt <= 4)
+    rmsnorm_long_kernel<T, 4><<<g, block, 0, st>>>(src, dst, wt, (int)cols, is, os, eps);
+  else
+    rmsnorm_long_kernel<T, 8><<<g, block, 0, st>>>(src, dst, wt, (int)cols, is, os, eps);
+  return FDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE (torch/rotemb.py:5-64), in place, positions = arange(seq).
+// One work item = 16 bytes of one head (interleaved) or 16 B from each half (neox).
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool NEOX>
+__global__ void __launch_bounds__(256) rope_kernel(T* __restrict__ q, T* __restrict__ k,
+                                                   const T* __restrict__ cs, int64_t batch,
+                                                   int64_t seq, int q_heads, int k_heads,
+                                                   int head_size, int64_t qbs, int64_t qts,
+                                                   int64_t kbs, int64_t kts, int64_t cs_stride) {
+  const int half = head_size >> 1;
+  const int items_per_head = NEOX ? (half >> 3) : (head_size >> 3);
+  const int heads = q_heads + k_heads;
+  const int64_t items_per_token = (int64_t)heads * items_per_head;
+  const int64_t total = batch * seq * items_per_token;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t tok = it / items_per_token;
+    const int rem = (int)(it - tok * items_per_token);
+    const int h = rem / items_per_head;
+    const int v = rem - h * items_per_head;
+    const int64_t b = tok / seq;
+    const int64_t s = tok - b * seq;
+    T* base = (h < q_heads) ? (q + b * qbs + s * qts + (int64_t)h * head_size)
+                            : (k + b * kbs + s * kts + (int64_t)(h - q_heads) * head_size);
+    const T* row = cs + s * cs_stride;
+    if (!NEOX) {
+      // elements 8v..8v+7 -> pairs 4v..4v+3
+      float x[8];
+      unpack8<T>(ldg128(base + v * 8), x);
+      const uint2 craw = *reinterpret_cast<const uint2*>(row + v * 4);
+      const uint2 sraw = *reinterpret_cast<const uint2*>(row + half + v * 4);
+      float c[4], sn[4];
+      if (sizeof(T) == 2 && Elem<T>::kId == FDM_BF16) {
+        c[0] = bf16lo(craw.x); c[1] = bf16hi(craw.x); c[2] = bf16lo(craw.y); c[3] = bf16hi(craw.y);
+        sn[0] = bf16lo(sraw.x); sn[1] = bf16hi(sraw.x); sn[2] = bf16lo(sraw.y); sn[3] = bf16hi(sraw.y);
+      } else {
+        c[0] = f16lo(craw.x); c[1] = f16hi(craw.x); c[2] = f16lo(craw.y); c[3] = f16hi(craw.y);
+        sn[0] = f16lo(sraw.x); sn[1] = f16hi(sraw.x); sn[2] = f16lo(sraw.y); sn[3] = f16hi(sraw.y);
+      }
+      float o[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float x1 = x[2 * p], x2 = x[2 * p + 1];
+        o[2 * p] = __fsub_rn(round_to<T>(__fmul_rn(x1, c[p])), round_to<T>(__fmul_rn(x2, sn[p])));
+        o[2 * p + 1] = __fadd_rn(round_to<T>(__fmul_rn(x2, c[p])), round_to<T>(__fmul_rn(x1, sn[p])));
+      }
+      stg128(base + v * 8, pack8<T>(o));
+    } else {
+      float x1[8], x2[8], c[8], sn[8];
+      unpack8<T>(ldg128(base + v * 8), x1);
+      unpack8<T>(ldg128(base + half + v * 8), x2);
+      unpack8<T>(ldg128(row + v * 8), c);
+      unpack8<T>(ldg128(row + half + v * 8), sn);
+      float o1[8], o2[8];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        o1[p] = __fsub_rn(round_to<T>(__fmul_rn(x1[p], c[p])), round_to<T>(__fmul_rn(x2[p], sn[p])));
+        o2[p] = __fadd_rn(round_to<T>(__fmul_rn(x2[p], c[p])), round_to<T>(__fmul_rn(x1[p], sn[p])));
+      }
+      stg128(base + v * 8, pack8<T>(o1));
+      stg128(base + half + v * 8, pack8<T>(o2));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gelu_and_mul (torch/gelumul.py:4-16): out = T( x1 * T(gelu_erf(x2)) ), x = [x1 | x2]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_mul_kernel(const T* __restrict__ in, T* __restrict__ out,
+                                                       int64_t rows, int64_t d, int64_t is,
+                                                       int64_t os) {
+  const int64_t vec_per_row = d >> 3;
+  const int64_t total = rows * vec_per_row;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = it / vec_per_row;
+    const int64_t v = it - r * vec_per_row;
+    float a[8], g[8], o[8];
+    unpack8<T>(ldg128_stream(in + r * is + v * 8), a);
+    unpack8<T>(ldg128_stream(in + r * is + d + v * 8), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a[j] * round_to<T>(gelu_erf(g[j]));
+    stg128(out + r * os + v * 8, pack8<T>(o));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gelu_mul_generic_kernel(const T* __restrict__ in,
+                                                               T* __restrict__ out, int64_t rows,
+                                                               int64_t d, int64_t is, int64_t os) {
+  const int64_t total = rows * d;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = it / d;
+    const int64_t c = it - r * d;
+    float a = Elem<T>::to_f(in[r * is + c]);
+    float g = Elem<T>::to_f(in[r * is + d + c]);
+    out[r * os + c] = Elem<T>::from_f(a * round_to<T>(gelu_erf(g)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ulysses layout helpers: [S, H, hd] <-> [P, S, H/P, hd], 16-byte vectors
+// ------------------------------------------------------------------------------------------------
+template <bool PACK>
+__global__ void __launch_bounds__(256) ulysses_heads_kernel(const uint8_t* __restrict__ src,
+                                                            uint8_t* __restrict__ dst,
+                                                            int64_t S, int H, int P,
+                                                            int64_t head_bytes,
+                                                            int64_t token_stride_bytes) {
+  // PACK:   src token-major strided [S, H*head_bytes], dst [P, S, (H/P)*head_bytes]
+  // !PACK:  src [P, S, (H/P)*head_bytes], dst token-major strided
+  const int hp = H / P;
+  const int64_t vec_per_head = head_bytes >> 4;
+  const int64_t vec_per_tok = (int64_t)H * vec_per_head;
+  const int64_t total = S * vec_per_tok;
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
+       it += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = it / vec_per_tok;
+    const int64_t rem = it - s * vec_per_tok;
+    const int h = (int)(rem / vec_per_head);
+    const int64_t v = rem - (int64_t)h * vec_per_head;
+    const int p = h / hp, hl = h - p * hp;
+    const int64_t strided = s * token_stride_bytes + (int64_t)h * head_bytes + v * 16;
+    const int64_t packed = (((int64_t)p * S + s) * hp + hl) * head_bytes + v * 16;
+    if (PACK) stg128(dst + packed, ldg128_stream(src + strided));
+    else stg128(dst + strided, ldg128_stream(src + packed));
+  }
+}
+
+static unsigned grid_for(int64_t items, int threads) {
+  int64_t blocks = (items + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+}  // namespace fdm
+
+using namespace fdm;
+
+extern "C" {
+
+int fdm_quant_fp8(const void* in, void* out, float* scale, int64_t rows, int64_t cols,
+                  int64_t in_row_stride, int in_dtype, void* stream) {
+  return quant_common(in, out, scale, nullptr, rows, cols, in_row_stride, in_dtype, FDM_ACT_NONE, 0,
+                      stream);
+}
+
+int fdm_quant_int8(const void* in, int8_t* out, float* scale, int32_t* azp, int64_t rows,
+                   int64_t cols, int64_t in_row_stride, int in_dtype, void* stream) {
+  return quant_common(in, out, scale, azp, rows, cols, in_row_stride, in_dtype, FDM_ACT_NONE,
+                      azp ? 2 : 1, stream);
+}
+
+int fdm_gelu_quant(const void* in, void* out, float* scale, int32_t* azp, int64_t rows,
+                   int64_t cols, int64_t in_row_stride, int act, int in_dtype, int out_dtype,
+                   void* stream) {
+  if (out_dtype == FDM_E4M3)
+    return quant_common(in, out, scale, nullptr, rows, cols, in_row_stride, in_dtype, act, 0, stream);
+  if (out_dtype == FDM_S8) {
+    FDM_REQUIRE(azp != nullptr, "gelu_quant: int8 output needs azp (asymmetric, as QLinear uses)");
+    return quant_common(in, out, scale, azp, rows, cols, in_row_stride, in_dtype, act, 2, stream);
+  }
+  set_error("gelu_quant: out_dtype must be FDM_E4M3 or FDM_S8");
+  return FDM_ERR_ARG;
+}
+
+int fdm_rms_norm(const void* in, void* out, const void* weight, int64_t rows, int64_t cols,
+                 int64_t in_row_stride, int64_t out_row_stride, float eps, int dtype, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(rows >= 0 && cols >= 0, "rms_norm: negative shape");
+  if (rows == 0 || cols == 0) return FDM_OK;
+  FDM_REQUIRE(in && out, "rms_norm: null pointer");
+  FDM_REQUIRE(in_row_stride >= cols && out_row_stride >= cols, "rms_norm: row stride < cols");
+  FDM_REQUIRE(rows <= 0x7fffffffLL, "rms_norm: too many rows");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FDM_BF16)
+    rc = launch_rmsnorm<__nv_bfloat16>(in, out, weight, rows, cols, in_row_stride, out_row_stride, eps, st);
+  else if (dtype == FDM_F16)
+    rc = launch_rmsnorm<__half>(in, out, weight, rows, cols, in_row_stride, out_row_stride, eps, st);
+  else {
+    set_error("rms_norm: dtype must be bf16 or f16");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  if (rc) return rc;
+  FDM_LAUNCH_CHECK("rms_norm kernel launch");
+  return FDM_OK;
+}
+
+int fdm_rope(void* q, void* k, const void* cos_sin, int64_t batch, int64_t seq, int q_heads,
+             int k_heads, int head_size, int64_t qbs, int64_t qts, int64_t kbs, int64_t kts,
+             int64_t cs_row_stride, int is_neox, int dtype, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (k == nullptr) k_heads = 0;
+  FDM_REQUIRE(batch >= 0 && seq >= 0 && q_heads >= 0 && k_heads >= 0, "rope: negative shape");
+  if (batch == 0 || seq == 0 || (q_heads + k_heads) == 0) return FDM_OK;
+  FDM_REQUIRE(q != nullptr || q_heads == 0, "rope: null q");
+  FDM_REQUIRE(cos_sin != nullptr, "rope: null cos_sin cache");
+  FDM_REQUIRE(head_size > 0 && head_size % (is_neox ? 16 : 8) == 0,
+              "rope: head_size %d must be a multiple of %d", head_size, is_neox ? 16 : 8);
+  FDM_REQUIRE(qts % 8 == 0 && qbs % 8 == 0 && kts % 8 == 0 && kbs % 8 == 0 && cs_row_stride % 4 == 0,
+              "rope: strides must keep 16-byte alignment");
+  FDM_REQUIRE((uintptr_t)q % 16 == 0 && (uintptr_t)k % 16 == 0 && (uintptr_t)cos_sin % 8 == 0,
+              "rope: pointers must be 16-byte aligned");
+  if (is_neox)
+    FDM_REQUIRE(cs_row_stride % 8 == 0 && (uintptr_t)cos_sin % 16 == 0,
+                "rope(neox): cache rows must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int iph = is_neox ? head_size / 16 : head_size / 8;
+  const int64_t total = batch * seq * (int64_t)(q_heads + k_heads) * iph;
+  const unsigned g = grid_for(total, 256);
+#define ROPE(T, NEOX)                                                                          \
+  rope_kernel<T, NEOX><<<g, 256, 0, st>>>((T*)q, (T*)k, (const T*)cos_sin, batch, seq, q_heads, \
+                                          k_heads, head_size, qbs, qts, kbs, kts, cs_row_stride)
+  if (dtype == FDM_BF16) {
+    if (is_neox) ROPE(__nv_bfloat16, true); else ROPE(__nv_bfloat16, false);
+  } else if (dtype == FDM_F16) {
+    if (is_neox) ROPE(__half, true); else ROPE(__half, false);
+  } else {
+    set_error("rope: dtype must be bf16 or f16");
+    return FDM_ERR_UNSUPPORTED;
+  }
+#undef ROPE
+  FDM_LAUNCH_CHECK("rope kernel launch");
+  return FDM_OK;
+}
+
+int fdm_gelu_and_mul(const void* in, void* out, int64_t rows, int64_t d, int64_t is, int64_t os,
+                     int dtype, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(rows >= 0 && d >= 0, "gelu_and_mul: negative shape");
+  if (rows == 0 || d == 0) return FDM_OK;
+  FDM_REQUIRE(in && out, "gelu_and_mul: null pointer");
+  FDM_REQUIRE(is >= 2 * d && os >= d, "gelu_and_mul: row stride too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec_ok = (d % 8 == 0) && (is % 8 == 0) && (os % 8 == 0) && ((uintptr_t)in % 16 == 0) &&
+                      ((uintptr_t)out % 16 == 0);
+  if (dtype == FDM_BF16) {
+    if (vec_ok)
+      gelu_mul_kernel<__nv_bfloat16><<<grid_for(rows * (d / 8), 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, d, is, os);
+    else
+      gelu_mul_generic_kernel<__nv_bfloat16><<<grid_for(rows * d, 256), 256, 0, st>>>(
+          (const __nv_bfloat16*)in, (__nv_bfloat16*)out, rows, d, is, os);
+  } else if (dtype == FDM_F16) {
+    if (vec_ok)
+      gelu_mul_kernel<__half><<<grid_for(rows * (d / 8), 256), 256, 0, st>>>(
+          (const __half*)in, (__half*)out, rows, d, is, os);
+    else
+      gelu_mul_generic_kernel<__half><<<grid_for(rows * d, 256), 256, 0, st>>>(
+          (const __half*)in, (__half*)out, rows, d, is, os);
+  } else {
+    set_error("gelu_and_mul: dtype must be bf16 or f16");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  FDM_LAUNCH_CHECK("gelu_and_mul kernel launch");
+  return FDM_OK;
+}
+
+static int ulysses_common(const void* src, void* dst, int64_t S, int H, int hd, int P,
+                          int64_t token_stride, int elem_size, bool pack, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(S >= 0 && H > 0 && hd > 0 && P > 0, "ulysses: bad shape");
+  FDM_REQUIRE(H % P == 0, "ulysses: heads (%d) not divisible by ranks (%d)", H, P);
+  FDM_REQUIRE(elem_size == 1 || elem_size == 2 || elem_size == 4, "ulysses: elem_size");
+  const int64_t head_bytes = (int64_t)hd * elem_size;
+  FDM_REQUIRE(head_bytes % 16 == 0 && (token_stride * elem_size) % 16 == 0,
+              "ulysses: head / token stride must be multiples of 16 bytes");
+  FDM_REQUIRE((uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "ulysses: alignment");
+  if (S == 0) return FDM_OK;
+  FDM_REQUIRE(src && dst, "ulysses: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = S * H * (head_bytes / 16);
+  const unsigned g = grid_for(total, 256);
+  if (pack)
+    ulysses_heads_kernel<true><<<g, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, S, H, P,
+                                                  head_bytes, token_stride * elem_size);
+  else
+    ulysses_heads_kernel<false><<<g, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, S, H, P,
+                                                   head_bytes, token_stride * elem_size);
+  FDM_LAUNCH_CHECK("ulysses layout kernel launch");
+  return FDM_OK;
+}
+
+int fdm_ulysses_pack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
+                           int64_t src_token_stride, int elem_size, void* stream) {
+  return ulysses_common(src, dst, S_local, H, hd, P, src_token_stride, elem_size, true, stream);
+}
+
+int fdm_ulysses_unpack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
+                             int64_t dst_token_stride, int elem_size, void* stream) {
+  return ulysses_common(src, dst, S_local, H, hd, P, dst_token_stride, elem_size, false, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+// Family 1: W8A8 GEMM for B200 -- FP8 (e4m3 x e4m3 -> f32) and INT8 (s8 x s8 -> s32) with FastDM's
+// per-token (row) x per-channel (column) scaling, INT8 asymmetric zero-point correction, bias and an
+// optional GELU, as one persistent warp-specialised tcgen05 kernel:
+//
+//   warp 0   : TMA producer  -- A [M,K] and B^T [N,K] tiles (128 B of K per stage row, 128B swizzle)
+//              into a STAGES-deep shared-memory ring, mbarrier complete_tx signalling
+//   warp 1   : MMA issuer    -- one elected thread issues tcgen05.mma (kind::f8f6f4 / kind::i8),
+//              accumulators live in TMEM (2 x BN columns, double buffered across tiles);
+//              tcgen05.commit releases smem stages and publishes finished accumulators
+//   warps 2-5: epilogue      -- tcgen05.ld the 128 x BN accumulator (one row per thread), apply
+//              sA[m]*sB[n] (+azp rank-1 correction) (+bias) (+GELU), round, 16-byte global stores.
+//              Runs concurrently with the next tile's main loop.
+//
+// Numerics follow fastdm/kernel/torch/matrixmul.py (the parity oracle):
+//   fp8 : out = T( (acc*sA)*sB + bias )                                     (:33, torch._scaled_mm)
+//   int8: out = T( T( float(acc - azp*azp_adj) * (sA*sB) ) + bias )         (:67-74)
+// Reference CUDA path being replaced: csrc/torch_bindings.cpp:24-160 -> csrc/gemm/*.cu (CUTLASS).
+#include "sm100.cuh"
+
+namespace fdm {
+using namespace sm100;
+
+constexpr int kBM = 128;          // rows per tile (UMMA M, cta_group::1)
+constexpr int kBK = 128;          // bytes (= 8-bit elements) of K per stage: one 128B swizzle row
+constexpr int kUmmaK = 32;        // K per tcgen05.mma for 8-bit operands
+constexpr int kGemmThreads = 192; // 6 warps
+constexpr int kEpiThreads = 128;
+constexpr int kGroupM = 16;       // m-tiles per rasterisation group (L2 reuse of B)
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = kBM * kBK;
+  static constexpr int kBBytes = BN * kBK;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kRing = kStages * kStageBytes;
+  // epilogue per-column parameters: scale_b, bias, azp_adj
+  static constexpr int kEpiOff = kRing;
+  static constexpr int kEpiBytes = 3 * BN * 4;
+  static constexpr int kBarOff = kEpiOff + kEpiBytes;
+  static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = 2 * BN;                    // 512 / 256 / 128
+};
+
+struct GemmParams {
+  const float* scale_a;
+  const float* scale_b;
+  const int32_t* azp_adj;
+  const int32_t* azp;
+  const void* bias;
+  void* d;
+  int M, N, K;
+  int64_t ldd;
+  int out_dtype;
+  int act;
+  int tiles_m, tiles_n;
+  int vec_store;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int group_size = kGroupM * tiles_n;
+  const int g = t / group_size;
+  const int first_m = g * kGroupM;
+  const int gm = min(kGroupM, tiles_m - first_m);
+  const int r = t - g * group_size;
+  tm = first_m + r % gm;
+  tn = r / gm;
+}
+
+template <bool INT8, int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  float* s_sb = reinterpret_cast<float*>(smem + S::kEpiOff);
+  float* s_bias = s_sb + BN;
+  int32_t* s_adj = reinterpret_cast<int32_t*>(s_bias + BN);
+  const uint32_t bar_base = base + S::kBarOff;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S::kStages + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * S::kStages + 2 + a); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S::kBarOff + (2 * S::kStages + 4) * 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<1>(smem_u32(tmem_ptr_smem), S::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = (p.K + kBK - 1) / kBK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        const int m0 = tm * kBM, n0 = tn * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = base + stage * S::kStageBytes;
+          const uint32_t sb = sa + S::kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m0);
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n0);
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        const int n0 = tn * BN;
+        int n_eff = min(BN, p.N - n0);
+        n_eff = (n_eff + 15) & ~15;
+        const uint32_t idesc =
+            INT8 ? make_idesc(kFmtS8, kFmtS8, kAccS32, kBM, (uint32_t)n_eff)
+                 : make_idesc(kFmtE4M3, kFmtE4M3, kAccF32, kBM, (uint32_t)n_eff);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + stage * S::kStageBytes;
+          const uint64_t adesc = make_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = make_desc_kmajor_sw128(sa + S::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k) {
+            // advancing K inside the 128B swizzle row: +32 bytes -> +2 in the (>>4) address field
+            umma_ss<INT8 ? MmaKind::I8 : MmaKind::F8F6F4, 1>(d_tmem, adesc + 2u * k, bdesc + 2u * k,
+                                                              idesc, (uint32_t)((kb | k) != 0));
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == S::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(tfull_bar(acc));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps =====================
+    const int epi_tid = threadIdx.x - 64;
+    const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are this warp's
+    const int row_in_tile = lane_group * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int tm, tn;
+      tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+      const int m0 = tm * kBM, n0 = tn * BN;
+      named_bar_sync(1, kEpiThreads);
+      for (int i = epi_tid; i < BN; i += kEpiThreads) {
+        const int col = n0 + i;
+        const bool ok = col < p.N;
+        s_sb[i] = ok ? p.scale_b[col] : 0.f;
+        float b = 0.f;
+        if (ok && p.bias != nullptr) {
+          b = (p.out_dtype == FDM_BF16)
+                  ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[col])
+                  : __half2float(reinterpret_cast<const __half*>(p.bias)[col]);
+        }
+        s_bias[i] = b;
+        if (INT8) s_adj[i] = (ok && p.azp_adj != nullptr) ? p.azp_adj[col] : 0;
+      }
+      named_bar_sync(1, kEpiThreads);
+
+      const int row = m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+      const float sa = row_ok ? p.scale_a[row] : 0.f;
+      int zp = 0;
+      if (INT8) zp = (row_ok && p.azp != nullptr) ? p.azp[row] : 0;
+      const bool has_bias = p.bias != nullptr;
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BN);
+      const int n_valid = min(BN, p.N - n0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c * 32 >= n_valid) break;
+        uint32_t r[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float sb = s_sb[c * 32 + j];
+          const float bs = s_bias[c * 32 + j];
+          float x;
+          if (INT8) {
+            const int a = (int)r[j] - zp * s_adj[c * 32 + j];
+            x = (float)a * (sa * sb);
+            if (has_bias) {
+              // oracle rounds to the output dtype before the bias add (matrixmul.py:72-74)
+              x = (p.out_dtype == FDM_BF16) ? round_to<__nv_bfloat16>(x) : round_to<__half>(x);
+              x = x + bs;
+            }
+          } else {
+            x = (__uint_as_float(r[j]) * sa) * sb + bs;
+          }
+          v[j] = x;
+        }
+        if (p.act != FDM_ACT_NONE) {
+          // unfused reference: GEMM output is rounded to T, then F.gelu runs on that tensor
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = (p.out_dtype == FDM_BF16) ? round_to<__nv_bfloat16>(v[j]) : round_to<__half>(v[j]);
+            v[j] = (p.act == FDM_ACT_GELU_TANH) ? gelu_tanh(x) : gelu_erf(x);
+          }
+        }
+        if (row_ok) {
+          const int col0 = n0 + c * 32;
+          if (p.vec_store) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.N) {
+                U128 o;
+                if (p.out_dtype == FDM_BF16) {
+                  o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                  o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                  o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                  o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+                } else {
+                  o.x = pack_f16(v[q * 8 + 0], v[q * 8 + 1]);
+                  o.y = pack_f16(v[q * 8 + 2], v[q * 8 + 3]);
+                  o.z = pack_f16(v[q * 8 + 4], v[q * 8 + 5]);
+                  o.w = pack_f16(v[q * 8 + 6], v[q * 8 + 7]);
+                }
+                stg128(dst + q * 8, o);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col0 + j < p.N) {
+                if (p.out_dtype == FDM_BF16)
+                  reinterpret_cast<__nv_bfloat16*>(p.d)[(int64_t)row * p.ldd + col0 + j] =
+                      __float2bfloat16_rn(v[j]);
+                else
+                  reinterpret_cast<__half*>(p.d)[(int64_t)row * p.ldd + col0 + j] =
+                      __float2half_rn(v[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, S::kTmemCols);
+  }
+}
+
+template <bool INT8, int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t st) {
+  using S = GemmSmem<BN>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  FDM_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set[dev] = true;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  gemm_w8a8_kernel<INT8, BN><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  FDM_LAUNCH_CHECK("gemm_w8a8 kernel launch");
+  return FDM_OK;
+}
+
+static int gemm_common(bool int8, const void* a, const void* b, const float* scale_a,
+                       const float* scale_b, const int32_t* azp_adj, const int32_t* azp,
+                       const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
+                       int64_t ldb, int64_t ldd, int out_dtype, int act, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(M >= 0 && N >= 0 && K > 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)M,
+              (long long)N, (long long)K);
+  if (M == 0 || N == 0) return FDM_OK;
+  FDM_REQUIRE(a && b && scale_a && scale_b && d, "gemm: null pointer");
+  FDM_REQUIRE(out_dtype == FDM_BF16 || out_dtype == FDM_F16, "gemm: out_dtype must be bf16 or f16");
+  FDM_REQUIRE(act >= FDM_ACT_NONE && act <= FDM_ACT_GELU_ERF, "gemm: unknown activation %d", act);
+  FDM_REQUIRE(K % 16 == 0, "gemm: K (%lld) must be a multiple of 16", (long long)K);
+  FDM_REQUIRE(N % 8 == 0, "gemm: N (%lld) must be a multiple of 8", (long long)N);
+  FDM_REQUIRE(lda >= K && ldb >= K && ldd >= N, "gemm: leading dimension too small");
+  FDM_REQUIRE(lda % 16 == 0 && ldb % 16 == 0, "gemm: lda/ldb must be multiples of 16 bytes");
+  FDM_REQUIRE((uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0,
+              "gemm: a and b must be 16-byte aligned");
+  FDM_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "gemm: dimension too large");
+  FDM_REQUIRE((azp == nullptr) == (azp_adj == nullptr), "gemm: azp and azp_adj come together");
+
+  // tile width: widest tile that still gives every SM work
+  const int sms = num_sms();
+  const int64_t tiles_m = (M + kBM - 1) / kBM;
+  int bn = 256;
+  if (tiles_m * ((N + 255) / 256) < sms) bn = 128;
+  if (bn == 128 && tiles_m * ((N + 127) / 128) < sms) bn = 64;
+  if (N <= 64) bn = 64;
+  else if (N <= 128 && bn > 128) bn = 128;
+  const int64_t tiles_n = (N + bn - 1) / bn;
+  FDM_REQUIRE(tiles_m * tiles_n < (1LL << 31), "gemm: too many tiles");
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)lda};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)kBM};
+    rc = make_tmap(&ta, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, a, dims, strides, box,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t strides[1] = {(uint64_t)ldb};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
+    rc = make_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b, dims, strides, box,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.scale_a = scale_a;
+  p.scale_b = scale_b;
+  p.azp_adj = azp_adj;
+  p.azp = azp;
+  p.bias = bias;
+  p.d = d;
+  p.M = (int)M;
+  p.N = (int)N;
+  p.K = (int)K;
+  p.ldd = ldd;
+  p.out_dtype = out_dtype;
+  p.act = act;
+  p.tiles_m = (int)tiles_m;
+  p.tiles_n = (int)tiles_n;
+  p.vec_store = (ldd % 8 == 0 && (uintptr_t)d % 16 == 0) ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int8) {
+    if (bn == 256) return launch_gemm<true, 256>(ta, tb, p, st);
+    if (bn == 128) return launch_gemm<true, 128>(ta, tb, p, st);
+    return launch_gemm<true, 64>(ta, tb, p, st);
+  }
+  if (bn == 256) return launch_gemm<false, 256>(ta, tb, p, st);
+  if (bn == 128) return launch_gemm<false, 128>(ta, tb, p, st);
+  return launch_gemm<false, 64>(ta, tb, p, st);
+}
+
+}  // namespace fdm
+
+extern "C" {
+
+int fdm_gemm_fp8(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                 const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldd, int out_dtype, int act, void* stream) {
+  return fdm::gemm_common(false, a, b, scale_a, scale_b, nullptr, nullptr, bias, d, M, N, K, lda,
+                          ldb, ldd, out_dtype, act, stream);
+}
+
+int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                  const int32_t* azp_adj, const int32_t* azp, const void* bias, void* d, int64_t M,
+                  int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int out_dtype,
+                  int act, void* stream) {
+  return fdm::gemm_common(true, a, b, scale_a, scale_b, azp_adj, azp, bias, d, M, N, K, lda, ldb,
+                          ldd, out_dtype, act, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,432 @@
+"""Torch-facing wrappers of the C ABI: each op is a `torch.library.custom_op` in the
+`fastdm_b200::` namespace that checks/allocates exactly as the reference's pybind layer and cuda
+backend did (csrc/torch_bindings.cpp:24-189, fastdm/kernel/cuda/*.py), then calls
+libfastdm_b200.so on the current CUDA stream.
+
+Names, argument meaning and error behaviour of the public functions at the bottom mirror
+fastdm/kernel/operators_set.py (reference), so they can be registered under `(op, "cuda")` in
+FastDM's kernel registry (see fastdm_b200/integration.py).
+"""
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, FDM_BF16, FDM_E4M3, FDM_F16, FDM_F32, FDM_S8
+
+_DT = {torch.bfloat16: FDM_BF16, torch.float16: FDM_F16, torch.float32: FDM_F32,
+       torch.float8_e4m3fn: FDM_E4M3, torch.int8: FDM_S8}
+_ACT = {None: ACT_NONE, "none": ACT_NONE, "gelu_tanh": ACT_GELU_TANH, "gelu-approximate": ACT_GELU_TANH,
+        "gelu_erf": ACT_GELU_ERF, "gelu": ACT_GELU_ERF}
+
+
+def _dt(t: torch.Tensor, what: str) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"fastdm_b200.{what}: unsupported dtype {t.dtype}") from None
+
+
+def _cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise RuntimeError(f"fastdm_b200.{what}: expected a CUDA tensor, got {t.device} "
+                           "(there is no CPU implementation)")
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------
+# quantisation
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fastdm_b200::quant_fp8", mutates_args=())
+def _quant_fp8(x: torch.Tensor, act: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    _cuda(x, "quantize_to_fp8")
+    if x.ndim != 2:
+        raise RuntimeError("fastdm_b200.quantize_to_fp8: input must be 2-D [tokens, channels]")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), device=x.device, dtype=torch.float8_e4m3fn)
+    scale = torch.empty((rows, 1), device=x.device, dtype=torch.float32)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        if act == ACT_NONE:
+            rc = lib.fdm_quant_fp8(x.data_ptr(), out.data_ptr(), scale.data_ptr(), rows, cols,
+                                   x.stride(0) if rows > 1 else cols, _dt(x, "quantize_to_fp8"), _stream(x))
+        else:
+            rc = lib.fdm_gelu_quant(x.data_ptr(), out.data_ptr(), scale.data_ptr(), None, rows, cols,
+                                    x.stride(0) if rows > 1 else cols, act, _dt(x, "gelu_quant"), FDM_E4M3, _stream(x))
+    _lib.check(rc, "quantize_to_fp8")
+    return out, scale
+
+
+@_quant_fp8.register_fake
+def _(x, act):
+    return (x.new_empty(x.shape, dtype=torch.float8_e4m3fn), x.new_empty((x.shape[0], 1), dtype=torch.float32))
+
+
+@torch.library.custom_op("fastdm_b200::quant_int8", mutates_args=())
+def _quant_int8(x: torch.Tensor, symmetric: bool, act: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    _cuda(x, "quantize_to_int8")
+    if x.ndim != 2:
+        raise RuntimeError("fastdm_b200.quantize_to_int8: input must be 2-D [tokens, channels]")
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), device=x.device, dtype=torch.int8)
+    scale = torch.empty((rows, 1), device=x.device, dtype=torch.float32)
+    # symmetric: an empty azp tensor stands for the reference's `None`
+    azp = torch.empty((0 if symmetric else rows, 1), device=x.device, dtype=torch.int32)
+    lib = _lib.load()
+    stride = x.stride(0) if rows > 1 else cols
+    with torch.cuda.device(x.device):
+        if act == ACT_NONE:
+            rc = lib.fdm_quant_int8(x.data_ptr(), out.data_ptr(), scale.data_ptr(),
+                                    None if symmetric else azp.data_ptr(), rows, cols, stride,
+                                    _dt(x, "quantize_to_int8"), _stream(x))
+        else:
+            if symmetric:
+                raise RuntimeError("fastdm_b200.gelu_quant: int8 output is asymmetric only")
+            rc = lib.fdm_gelu_quant(x.data_ptr(), out.data_ptr(), scale.data_ptr(), azp.data_ptr(), rows, cols,
+                                    stride, act, _dt(x, "gelu_quant"), FDM_S8, _stream(x))
+    _lib.check(rc, "quantize_to_int8")
+    return out, scale, azp
+
+
+@_quant_int8.register_fake
+def _(x, symmetric, act):
+    return (x.new_empty(x.shape, dtype=torch.int8), x.new_empty((x.shape[0], 1), dtype=torch.float32),
+            x.new_empty((0 if symmetric else x.shape[0], 1), dtype=torch.int32))
+
+
+# ------------------------------------------------------------------------------------------------
+# norms / rope / activation
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fastdm_b200::rms_norm", mutates_args=())
+def _rms_norm(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    _cuda(x, "rms_norm")
+    cols = x.shape[-1]
+    if weight is not None:
+        if weight.numel() != cols:
+            raise RuntimeError(f"fastdm_b200.rms_norm: weight has {weight.numel()} elements, last dim is {cols}")
+        if weight.dtype != x.dtype:
+            # reference torch backend: `input.to(scale.dtype) * scale` (kernel/torch/norm.py:21-23)
+            raise RuntimeError("fastdm_b200.rms_norm: weight dtype must equal input dtype")
+        weight = weight.contiguous()
+    # rows of the last dimension; accept any view whose leading dims collapse to one stride
+    xc = x if x.is_contiguous() else x.contiguous()  # callers always pass contiguous (layer/transformer.py:275-290)
+    out = torch.empty_like(xc)
+    rows = xc.numel() // cols if cols else 0
+    with torch.cuda.device(x.device):
+        rc = _lib.load().fdm_rms_norm(xc.data_ptr(), out.data_ptr(), _ptr(weight), rows, cols, cols, cols,
+                                      float(eps), _dt(x, "rms_norm"), _stream(x))
+    _lib.check(rc, "rms_norm")
+    return out
+
+
+@_rms_norm.register_fake
+def _(x, weight, eps):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+@torch.library.custom_op("fastdm_b200::rope_", mutates_args=("query", "key"))
+def _rope(query: torch.Tensor, key: torch.Tensor, head_size: int, cos_sin_cache: torch.Tensor,
+          is_neox: bool) -> None:
+    _cuda(query, "rotary_pos_embedding")
+    if query.ndim != 3 or key.ndim != 3:
+        raise RuntimeError("fastdm_b200.rotary_pos_embedding: query/key must be [batch, seq, heads*head_size]")
+    if query.stride(2) != 1 or key.stride(2) != 1:
+        raise RuntimeError("fastdm_b200.rotary_pos_embedding: last dimension must be contiguous (in-place op)")
+    b, s, qd = query.shape
+    kb, ks, kd = key.shape
+    if (kb, ks) != (b, s):
+        raise RuntimeError("fastdm_b200.rotary_pos_embedding: query and key must share batch and seq")
+    if qd % head_size or kd % head_size:
+        raise RuntimeError("fastdm_b200.rotary_pos_embedding: hidden size not a multiple of head_size")
+    if cos_sin_cache.ndim != 2 or cos_sin_cache.shape[0] < s or cos_sin_cache.shape[1] != head_size:
+        raise RuntimeError("fastdm_b200.rotary_pos_embedding: cos_sin_cache must be [>=seq, head_size]")
+    cs = cos_sin_cache
+    if cs.dtype != query.dtype or cs.stride(1) != 1:
+        cs = cs.to(query.dtype).contiguous()  # reference: cos/sin `.to(x.dtype)` (kernel/torch/rotemb.py:40-41)
+    with torch.cuda.device(query.device):
+        rc = _lib.load().fdm_rope(query.data_ptr(), key.data_ptr(), cs.data_ptr(), b, s, qd // head_size,
+                                  kd // head_size, head_size, query.stride(0), query.stride(1),
+                                  key.stride(0), key.stride(1), cs.stride(0), 1 if is_neox else 0,
+                                  _dt(query, "rotary_pos_embedding"), _stream(query))
+    _lib.check(rc, "rotary_pos_embedding")
+
+
+@torch.library.custom_op("fastdm_b200::gelu_and_mul", mutates_args=())
+def _gelu_and_mul(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x, "gelu_and_mul")
+    if x.shape[-1] % 2:
+        raise RuntimeError("fastdm_b200.gelu_and_mul: last dimension must be even")
+    d = x.shape[-1] // 2
+    xc = x if x.is_contiguous() else x.contiguous()
+    out = torch.empty(x.shape[:-1] + (d,), device=x.device, dtype=x.dtype)
+    rows = xc.numel() // (2 * d) if d else 0
+    with torch.cuda.device(x.device):
+        rc = _lib.load().fdm_gelu_and_mul(xc.data_ptr(), out.data_ptr(), rows, d, 2 * d, d,
+                                          _dt(x, "gelu_and_mul"), _stream(x))
+    _lib.check(rc, "gelu_and_mul")
+    return out
+
+
+@_gelu_and_mul.register_fake
+def _(x):
+    return x.new_empty(x.shape[:-1] + (x.shape[-1] // 2,))
+
+
+# ------------------------------------------------------------------------------------------------
+# W8A8 GEMMs
+# ------------------------------------------------------------------------------------------------
+def _check_mm(a, b, scale_a, scale_b, out_dtype, bias, what, qdtype):
+    # the checks of csrc/torch_bindings.cpp:31-58 / :93-123
+    _cuda(a, what)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[0]:
+        raise RuntimeError(f"fastdm_b200.{what}: shapes {tuple(a.shape)} x {tuple(b.shape)} do not multiply")
+    if a.dtype != qdtype or b.dtype != qdtype:
+        raise RuntimeError(f"fastdm_b200.{what}: a and b must be {qdtype}")
+    if a.stride(1) != 1:
+        raise RuntimeError(f"fastdm_b200.{what}: a must be row-major")
+    if b.stride(0) != 1:
+        raise RuntimeError(f"fastdm_b200.{what}: b must be column-major (b.stride(0) == 1)")
+    m, k = a.shape
+    n = b.shape[1]
+    if scale_a.numel() != m or scale_b.numel() != n:
+        raise RuntimeError(f"fastdm_b200.{what}: scale_a must have M and scale_b N elements")
+    if scale_a.dtype != torch.float32 or scale_b.dtype != torch.float32:
+        raise RuntimeError(f"fastdm_b200.{what}: scales must be float32")
+    if not (scale_a.is_contiguous() and scale_b.is_contiguous()):
+        raise RuntimeError(f"fastdm_b200.{what}: scales must be contiguous")
+    if out_dtype not in (torch.bfloat16, torch.float16):
+        raise RuntimeError(f"fastdm_b200.{what}: out_dtype must be bfloat16 or float16")
+    if bias is not None:
+        if bias.numel() != n or not bias.is_contiguous() or bias.dtype != out_dtype:
+            raise RuntimeError(f"fastdm_b200.{what}: bias must be contiguous [N] of out_dtype")
+    return m, n, k
+
+
+@torch.library.custom_op("fastdm_b200::gemm_fp8", mutates_args=())
+def _gemm_fp8(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
+              out_dtype: torch.dtype, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    m, n, k = _check_mm(a, b, scale_a, scale_b, out_dtype, bias, "fp8_matmul", torch.float8_e4m3fn)
+    out = torch.empty((m, n), device=a.device, dtype=out_dtype)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().fdm_gemm_fp8(a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(),
+                                      _ptr(bias), out.data_ptr(), m, n, k,
+                                      a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k, n,
+                                      _DT[out_dtype], act, _stream(a))
+    _lib.check(rc, "fp8_matmul")
+    return out
+
+
+@_gemm_fp8.register_fake
+def _(a, b, scale_a, scale_b, out_dtype, bias, act):
+    return a.new_empty((a.shape[0], b.shape[1]), dtype=out_dtype)
+
+
+@torch.library.custom_op("fastdm_b200::gemm_int8", mutates_args=())
+def _gemm_int8(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
+               out_dtype: torch.dtype, azp_adj: Optional[torch.Tensor], azp: Optional[torch.Tensor],
+               bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
+    m, n, k = _check_mm(a, b, scale_a, scale_b, out_dtype, bias, "int8_matmul", torch.int8)
+    if (azp is None) != (azp_adj is None):
+        raise RuntimeError("fastdm_b200.int8_matmul: azp and azp_adj must be given together")
+    if azp is not None:
+        if azp.numel() != m or azp_adj.numel() != n:
+            raise RuntimeError("fastdm_b200.int8_matmul: azp must have M and azp_adj N elements")
+        if azp.dtype != torch.int32 or azp_adj.dtype != torch.int32:
+            raise RuntimeError("fastdm_b200.int8_matmul: azp / azp_adj must be int32")
+        if not (azp.is_contiguous() and azp_adj.is_contiguous()):
+            raise RuntimeError("fastdm_b200.int8_matmul: azp / azp_adj must be contiguous")
+    out = torch.empty((m, n), device=a.device, dtype=out_dtype)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().fdm_gemm_int8(a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(),
+                                       _ptr(azp_adj), _ptr(azp), _ptr(bias), out.data_ptr(), m, n, k,
+                                       a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k, n,
+                                       _DT[out_dtype], act, _stream(a))
+    _lib.check(rc, "int8_matmul")
+    return out
+
+
+@_gemm_int8.register_fake
+def _(a, b, scale_a, scale_b, out_dtype, azp_adj, azp, bias, act):
+    return a.new_empty((a.shape[0], b.shape[1]), dtype=out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fastdm_b200::attn_fwd", mutates_args=())
+def _attn_fwd(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_heads: int, head_dim: int,
+              scale: float, block_mask: Optional[torch.Tensor], mask_bq: int, mask_bk: int) -> torch.Tensor:
+    what = "scaled_dot_product_attention"
+    _cuda(query, what)
+    if query.ndim != 3 or key.ndim != 3 or value.ndim != 3:
+        raise RuntimeError(f"fastdm_b200.{what}: q/k/v must be [batch, seq, heads*head_dim]")
+    b, sq, c = query.shape
+    sk = key.shape[1]
+    if c != num_heads * head_dim or key.shape[2] != c or value.shape[2] != c:
+        raise RuntimeError(f"fastdm_b200.{what}: hidden size must be num_heads*head_dim for q, k and v (MHA)")
+    if key.shape[0] != b or value.shape[0] != b or value.shape[1] != sk:
+        raise RuntimeError(f"fastdm_b200.{what}: batch / kv length mismatch")
+    if not (query.dtype == key.dtype == value.dtype):
+        raise RuntimeError(f"fastdm_b200.{what}: q/k/v dtypes differ")
+    ts = []
+    for t in (query, key, value):
+        # last-dim slices of a fused qkv projection are legal (layer/transformer.py:269,300)
+        if t.stride(2) != 1 or (t.stride(1) * t.element_size()) % 16 or (t.stride(0) * t.element_size()) % 16 \
+                or t.data_ptr() % 16:
+            t = t.contiguous()
+        ts.append(t)
+    q, k, v = ts
+    out_dtype = torch.float16 if query.dtype == torch.float16 else torch.bfloat16
+    out = torch.empty((b, sq, c), device=query.device, dtype=out_dtype)
+    if block_mask is not None:
+        block_mask = block_mask.to(torch.int8).contiguous()
+        nbq, nbk = -(-sq // mask_bq), -(-sk // mask_bk)
+        if tuple(block_mask.shape) != (b, num_heads, nbq, nbk):
+            raise RuntimeError(f"fastdm_b200.{what}: sparse_mask must be {(b, num_heads, nbq, nbk)}, "
+                               f"got {tuple(block_mask.shape)}")
+    with torch.cuda.device(query.device):
+        rc = _lib.load().fdm_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(block_mask),
+                                      b, sq, sk, num_heads, head_dim,
+                                      q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                      mask_bq, mask_bk, float(scale), _dt(q, what), _stream(q))
+    _lib.check(rc, what)
+    return out
+
+
+@_attn_fwd.register_fake
+def _(query, key, value, num_heads, head_dim, scale, block_mask, mask_bq, mask_bk):
+    return query.new_empty(query.shape, dtype=torch.float16 if query.dtype == torch.float16 else torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------
+# Ulysses layout helpers
+# ------------------------------------------------------------------------------------------------
+def ulysses_pack_heads(x: torch.Tensor, num_heads: int, world: int) -> torch.Tensor:
+    """[S, H*hd] (row stride free) -> [P, S, H/P * hd] contiguous send buffer."""
+    _cuda(x, "ulysses_pack_heads")
+    s, c = x.shape
+    hd = c // num_heads
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    out = torch.empty((world, s, c // world), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().fdm_ulysses_pack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, hd, world,
+                                                x.stride(0) if s > 1 else c, x.element_size(), _stream(x))
+    _lib.check(rc, "ulysses_pack_heads")
+    return out
+
+
+def ulysses_unpack_heads(x: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[P, S, H/P * hd] received chunks -> [S, H*hd]."""
+    _cuda(x, "ulysses_unpack_heads")
+    world, s, cp = x.shape
+    c = cp * world
+    hd = c // num_heads
+    x = x.contiguous()
+    if out is None:
+        out = torch.empty((s, c), device=x.device, dtype=x.dtype)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().fdm_ulysses_unpack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, hd, world,
+                                                  out.stride(0) if s > 1 else c, x.element_size(), _stream(x))
+    _lib.check(rc, "ulysses_unpack_heads")
+    return out
+
+
+# ================================================================================================
+# Public op API -- same names and signatures as fastdm/kernel/operators_set.py (reference)
+# ================================================================================================
+def rms_norm(input: torch.Tensor, scale: Optional[torch.Tensor], eps: float) -> torch.Tensor:
+    """operators_set.py:9-21; numerics of kernel/torch/norm.py:5-27."""
+    return torch.ops.fastdm_b200.rms_norm(input, scale, eps)
+
+
+def rotary_pos_embedding(query: torch.Tensor, key: torch.Tensor, head_size: int, cos_sin_cache: torch.Tensor,
+                         is_neox: bool = False):
+    """operators_set.py:23-52; in place on query and key, returns None (kernel/torch/rotemb.py:62-64)."""
+    torch.ops.fastdm_b200.rope_(query, key, head_size, cos_sin_cache, is_neox)
+    return
+
+
+def gelu_and_mul(input: torch.Tensor) -> torch.Tensor:
+    """operators_set.py:54-67: x[..., :d] * gelu(x[..., d:])."""
+    return torch.ops.fastdm_b200.gelu_and_mul(input)
+
+
+def quantize_to_int8(input: torch.Tensor, symmetric: bool = True
+                     ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+    """operators_set.py:69-84; returns (int8 codes, scales [M,1], azp [M,1] int32 or None)."""
+    q, s, zp = torch.ops.fastdm_b200.quant_int8(input, symmetric, ACT_NONE)
+    return q, s, (None if symmetric else zp)
+
+
+def quantize_to_fp8(input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """operators_set.py:86-100; returns (e4m3 codes, scales [M,1])."""
+    return torch.ops.fastdm_b200.quant_fp8(input, ACT_NONE)
+
+
+def fp8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
+               out_dtype: torch.dtype, bias: Optional[torch.Tensor] = None, act: Optional[str] = None) -> torch.Tensor:
+    """operators_set.py:102-124 (+ optional fused GELU epilogue `act`)."""
+    if b.shape[0] % 16 or b.shape[1] % 16:  # kernel/cuda/matrixmul.py:31
+        raise AssertionError("fp8_matmul: K and N must be multiples of 16")
+    return torch.ops.fastdm_b200.gemm_fp8(a, b, scale_a, scale_b, out_dtype, bias, _ACT[act])
+
+
+def int8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
+                out_dtype: torch.dtype, azp_adj: Optional[torch.Tensor], azp: Optional[torch.Tensor],
+                bias: Optional[torch.Tensor] = None, act: Optional[str] = None) -> torch.Tensor:
+    """operators_set.py:126-152 (+ optional fused GELU epilogue `act`)."""
+    if b.shape[0] % 16 or b.shape[1] % 16:  # kernel/cuda/matrixmul.py:65
+        raise AssertionError("int8_matmul: K and N must be multiples of 16")
+    return torch.ops.fastdm_b200.gemm_int8(a, b, scale_a, scale_b, out_dtype, azp_adj, azp, bias, _ACT[act])
+
+
+def scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_q_heads: int,
+                                 num_kv_heads: int, head_dim: int, is_causal: bool = False,
+                                 scale: Optional[float] = None) -> torch.Tensor:
+    """operators_set.py:154-179. Non-causal MHA only (every hot-path call: layer/transformer.py:149,300)."""
+    if is_causal:
+        raise NotImplementedError("fastdm_b200.scaled_dot_product_attention: is_causal=True is not on the DiT hot path")
+    if num_q_heads != num_kv_heads:
+        raise NotImplementedError("fastdm_b200.scaled_dot_product_attention: GQA/MQA is not on the DiT hot path")
+    if scale is None:
+        scale = head_dim ** -0.5
+    return torch.ops.fastdm_b200.attn_fwd(query, key, value, num_q_heads, head_dim, scale, None, 128, 64)
+
+
+def sparse_scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
+                                        num_q_heads: int, num_kv_heads: int, head_dim: int, is_causal: bool = False,
+                                        scale: Optional[float] = None, sparse_mask: Optional[torch.Tensor] = None,
+                                        block_q: int = 128, block_k: int = 64) -> torch.Tensor:
+    """operators_set.py:181-208. sparse_mask [B, H, ceil(Sq/128), ceil(Sk/64)], 1 = compute, 0 = skip
+    (non-sm90 block geometry of kernel/cuda/attention.py:92-94)."""
+    if is_causal:
+        raise NotImplementedError("fastdm_b200.sparse_scaled_dot_product_attention: is_causal=True unsupported")
+    if num_q_heads != num_kv_heads:
+        raise NotImplementedError("fastdm_b200.sparse_scaled_dot_product_attention: GQA/MQA unsupported")
+    if scale is None:
+        scale = head_dim ** -0.5
+    return torch.ops.fastdm_b200.attn_fwd(query, key, value, num_q_heads, head_dim, scale, sparse_mask,
+                                          block_q, block_k)
+
+
+# fused extras used by the host-side layers (fastdm_b200/layers.py)
+def gelu_quantize_to_fp8(input: torch.Tensor, approximate: str = "tanh"):
+    """quantize_to_fp8(F.gelu(x, approximate=...)) in one pass over HBM."""
+    return torch.ops.fastdm_b200.quant_fp8(input, ACT_GELU_TANH if approximate == "tanh" else ACT_GELU_ERF)
+
+
+def gelu_quantize_to_int8(input: torch.Tensor, approximate: str = "tanh"):
+    """quantize_to_int8(F.gelu(x, approximate=...), symmetric=False) in one pass over HBM."""
+    return torch.ops.fastdm_b200.quant_int8(input, False, ACT_GELU_TANH if approximate == "tanh" else ACT_GELU_ERF)

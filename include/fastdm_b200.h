@@ -1,0 +1,174 @@
+/*
+ * fastdm_b200.h -- C ABI of libfastdm_b200.so: the B200-native (sm_100a) DiT transformer-block
+ * hot path that replaces FastDM's pybind module `fastdm.cuda_ops`
+ * (reference: csrc/torch_bindings.cpp:191-201, csrc/include/ops.h:9-32).
+ *
+ * Conventions
+ *  - plain pointers + sizes only; every pointer is a DEVICE pointer unless stated otherwise.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - every entry point returns 0 on success, a negative FDM_ERR_* otherwise, and never throws;
+ *    fdm_last_error() returns a thread-local human-readable message for the last failure
+ *    (reference convention: TORCH_CHECK -> RuntimeError, csrc/torch_bindings.cpp:31-61; the Python
+ *    wrappers in fastdm_b200/ops.py raise RuntimeError from the code + message).
+ *  - no state is kept between calls except a per-device cache of TMA descriptors / attribute
+ *    settings; all entry points are thread-safe under the caller's usual "one stream at a time".
+ *  - there is NO CPU fallback: on a device that is not compute capability 10.x every compute entry
+ *    point returns FDM_ERR_ARCH.
+ */
+#ifndef FASTDM_B200_H_
+#define FASTDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDM_OK 0
+#define FDM_ERR_ARG (-1)     /* bad shape / alignment / null pointer                       */
+#define FDM_ERR_ARCH (-2)    /* device is not sm_100                                        */
+#define FDM_ERR_CUDA (-3)    /* a CUDA runtime / driver call failed (message has the detail) */
+#define FDM_ERR_UNSUPPORTED (-4)
+
+/* element types of activations / outputs */
+#define FDM_BF16 0
+#define FDM_F16 1
+#define FDM_F32 2
+#define FDM_E4M3 3
+#define FDM_S8 4
+
+/* GEMM epilogue activation (applied after scales + bias, before the output rounding) */
+#define FDM_ACT_NONE 0
+#define FDM_ACT_GELU_TANH 1 /* F.gelu(approximate="tanh"): fastdm/layer/activations.py:38-41 */
+#define FDM_ACT_GELU_ERF 2  /* F.gelu exact:              fastdm/model/flux.py:61             */
+
+const char* fdm_last_error(void);
+/* "fastdm_b200 <version> sm_100a" */
+const char* fdm_version(void);
+/* 0 if device `dev` can run the kernels (cc 10.x), FDM_ERR_ARCH otherwise. */
+int fdm_check_device(int dev);
+
+/* ---------------------------------------------------------------------------------------------
+ * Family 3: memory-bound ops (reference: csrc/elmwise_ops.cu; semantics follow the torch backend,
+ * fastdm/kernel/torch/*.py, which is the parity oracle -- see SURVEY.md section 8(a)).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Per-token dynamic FP8 (e4m3fn) quantisation.
+ * Replaces fp8_quant_(out, input, scale, None): csrc/elmwise_ops.cu:524-547, ops.h:12-14.
+ * Semantics: fastdm/kernel/torch/quantize.py:45-67 (bit-exact codes and scales).
+ *   in   [rows, cols] in_dtype (BF16|F16|F32), row stride in_row_stride elements, unit column stride
+ *   out  [rows, cols] e4m3, contiguous
+ *   scale[rows] fp32 */
+int fdm_quant_fp8(const void* in, void* out, float* scale, int64_t rows, int64_t cols,
+                  int64_t in_row_stride, int in_dtype, void* stream);
+
+/* Per-token dynamic INT8 quantisation, symmetric (azp == NULL) or asymmetric (azp != NULL).
+ * Replaces int8_quant_(out, input, scales, azp): csrc/elmwise_ops.cu:402-431, ops.h:9-11.
+ * Semantics: fastdm/kernel/torch/quantize.py:7-43 (bit-exact codes, scales and zero points). */
+int fdm_quant_int8(const void* in, int8_t* out, float* scale, int32_t* azp, int64_t rows,
+                   int64_t cols, int64_t in_row_stride, int in_dtype, void* stream);
+
+/* RMSNorm over the last dimension: out = dtype(x * rsqrt(mean(x^2) + eps)) * weight.
+ * Replaces rms_norm_(out, input, weight, eps): csrc/elmwise_ops.cu:433-449, ops.h:15-18.
+ * Semantics: fastdm/kernel/torch/norm.py:5-27. weight may be NULL (no scaling).
+ *   in/out [rows, cols], row strides in elements (out may alias in). */
+int fdm_rms_norm(const void* in, void* out, const void* weight, int64_t rows, int64_t cols,
+                 int64_t in_row_stride, int64_t out_row_stride, float eps, int dtype, void* stream);
+
+/* In-place rotary embedding on q and k with positions = arange(seq) (the only use on the hot
+ * path: fastdm/kernel/cuda/rotemb.py:36).
+ * Replaces rotary_emb_(positions, query, key, head_size, cos_sin_cache, is_neox):
+ * csrc/elmwise_ops.cu:451-522, ops.h:20-32. Semantics: fastdm/kernel/torch/rotemb.py:5-64
+ * (every product / sum rounded to `dtype`).
+ *   q [batch, seq, q_heads*head_size] with strides (q_batch_stride, q_token_stride, 1)
+ *   k [batch, seq, k_heads*head_size] likewise (k may be NULL)
+ *   cos_sin [>=seq, head_size] `dtype`, row stride cs_row_stride: cos(head_size/2) || sin(head_size/2) */
+int fdm_rope(void* q, void* k, const void* cos_sin, int64_t batch, int64_t seq, int q_heads,
+             int k_heads, int head_size, int64_t q_batch_stride, int64_t q_token_stride,
+             int64_t k_batch_stride, int64_t k_token_stride, int64_t cs_row_stride, int is_neox,
+             int dtype, void* stream);
+
+/* out[r, :d] = x[r, :d] * gelu_erf(x[r, d:2d])   (second half gated).
+ * The reference has no CUDA kernel for this op (fastdm/kernel/cuda/gelumul.py:17 raises; the
+ * dispatcher forces Triton, fastdm/kernel/operators_set.py:54). Semantics:
+ * fastdm/kernel/torch/gelumul.py:4-16. */
+int fdm_gelu_and_mul(const void* in, void* out, int64_t rows, int64_t d, int64_t in_row_stride,
+                     int64_t out_row_stride, int dtype, void* stream);
+
+/* Elementwise GELU (act = FDM_ACT_GELU_TANH | FDM_ACT_GELU_ERF) fused with the per-token FP8/INT8
+ * quantisation of the NEXT QLinear (the un-fused F.gelu + quant passes).
+ * out_dtype FDM_E4M3: scale[rows]; FDM_S8: scale[rows] + azp[rows] (asymmetric).
+ * Equals quant(gelu(x).to(dtype)) of the two reference ops bit for bit. */
+int fdm_gelu_quant(const void* in, void* out, float* scale, int32_t* azp, int64_t rows,
+                   int64_t cols, int64_t in_row_stride, int act, int in_dtype, int out_dtype,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Family 1: W8A8 GEMMs, per-token (row) activation scale x per-channel (column) weight scale.
+ * ------------------------------------------------------------------------------------------- */
+
+/* D[m,n] = out_dtype( act( sA[m]*sB[n]*sum_k A[m,k]*B[k,n] + bias[n] ) ), fp32 accumulation.
+ * Replaces fp8_scaled_mm_(a, b, scales_a, scales_b, out_dtype, bias): csrc/torch_bindings.cpp:24-84.
+ * Semantics: fastdm/kernel/torch/matrixmul.py:7-35.
+ *   a  [M,K] e4m3 row-major, row stride lda (bytes == elements), 16-byte aligned rows
+ *   b  [K,N] e4m3 COLUMN-major: element (k,n) at b[n*ldb + k] (reference: torch_bindings.cpp:36)
+ *   scale_a[M], scale_b[N] fp32; bias[N] in out_dtype or NULL; d [M,N] row-major, row stride ldd
+ *   out_dtype: FDM_BF16 | FDM_F16.   Requires K % 16 == 0, N % 8 == 0. */
+int fdm_gemm_fp8(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                 const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldd, int out_dtype, int act, void* stream);
+
+/* D[m,n] = out_dtype( (acc_i32[m,n] - azp[m]*azp_adj[n]) * sA[m]*sB[n] ) + bias[n]
+ * (rounded to out_dtype BEFORE the bias add, as the oracle does; azp/azp_adj NULL => symmetric).
+ * Replaces int8_scaled_mm_(a, b, scales_a, scales_b, out_dtype, azp_adj, azp, bias):
+ * csrc/torch_bindings.cpp:86-160. Semantics: fastdm/kernel/torch/matrixmul.py:37-74.
+ * Layouts as fdm_gemm_fp8 with int8 operands; azp_adj[N] int32 (weight column sums,
+ * fastdm/layer/qlinear.py:49), azp[M] int32. */
+int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                  const int32_t* azp_adj, const int32_t* azp, const void* bias, void* d, int64_t M,
+                  int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int out_dtype,
+                  int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Family 2: attention. Non-causal multi-head attention, token-major ("NHD") layouts.
+ * ------------------------------------------------------------------------------------------- */
+
+/* O = softmax(scale * Q K^T [+ block mask]) V.
+ * Replaces the `sdpa` / `sdpa_sparse` cuda-backend routes (fastdm/kernel/cuda/attention.py:149-261,
+ * i.e. cuDNN SDPA / sageattention / spas_sage_attn) and flash_attention_fp8_fwd_
+ * (csrc/torch_bindings.cpp:162-189). Semantics: fastdm/kernel/torch/attention.py:7-43 and the fp32
+ * reference tests/test_attention.py:23-63.
+ *   q [B, Sq, H, hd], k/v [B, Sk, H, hd]: element (b,s,h,d) at base + b*batch_stride + s*token_stride + h*hd + d
+ *   o [B, Sq, H, hd] contiguous (token stride H*hd), always BF16 (F16 when qkv_dtype is F16)
+ *   qkv_dtype: FDM_BF16 | FDM_F16 | FDM_E4M3 (fp8: per-tensor descale 1.0, P quantised to e4m3
+ *              unscaled -- the reference's only fp8 semantics, csrc/attention/interface.cu:262-270)
+ *   hd in {64, 128}
+ *   block_mask: NULL (dense) or int8 [B, H, ceil(Sq/mask_bq), ceil(Sk/mask_bk)], 1 = compute,
+ *               0 = skip (excluded from the softmax); mask_bq in {64,128}, mask_bk in {64,128}
+ *               (reference geometry: fastdm/kernel/cuda/attention.py:89-103). */
+int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o, const int8_t* block_mask,
+                 int64_t B, int64_t Sq, int64_t Sk, int H, int hd, int64_t q_batch_stride,
+                 int64_t q_token_stride, int64_t k_batch_stride, int64_t k_token_stride,
+                 int64_t v_batch_stride, int64_t v_token_stride, int mask_bq, int mask_bk,
+                 float scale, int qkv_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Family 4 helpers: Ulysses sequence-parallel layout kernels (no reference counterpart; the
+ * exchange itself is NCCL all-to-all issued from the host side, fastdm_b200/ulysses.py).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Pack src [S_local, H, hd] (token stride src_token_stride) into dst [P, S_local, H/P, hd]
+ * contiguous, i.e. chunk p holds heads [p*H/P, (p+1)*H/P): the send buffer of the pre-attention
+ * all-to-all. elem_size in bytes (1, 2 or 4); H % P == 0. */
+int fdm_ulysses_pack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
+                           int64_t src_token_stride, int elem_size, void* stream);
+
+/* Inverse of the above for the post-attention all-to-all: src [P, S_local, H/P, hd] (received
+ * chunks, chunk p = heads of rank p) -> dst [S_local, H, hd] with token stride dst_token_stride. */
+int fdm_ulysses_unpack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
+                             int64_t dst_token_stride, int elem_size, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTDM_B200_H_ */

@@ -1,0 +1,185 @@
+"""GPU-side diagnostics (run under gpurun): prints detailed error patterns for the tcgen05 kernels
+so a wrong descriptor / layout can be diagnosed from one trip. Not a test; not a benchmark."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fastdm_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+BF = torch.bfloat16
+out = {}
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gemm_patterns():
+    print("== GEMM structured patterns ==")
+    for (M, K, N) in ((128, 128, 64), (128, 128, 256), (128, 256, 256), (256, 512, 512), (130, 144, 48)):
+        # 1. all ones
+        a = torch.ones(M, K, device=DEV).to(torch.float8_e4m3fn)
+        b = torch.ones(N, K, device=DEV).to(torch.float8_e4m3fn).t()
+        s_m = torch.ones(M, 1, device=DEV)
+        s_n = torch.ones(N, 1, device=DEV)
+        y = ops.fp8_matmul(a, b, s_m, s_n, BF, None) if N % 16 == 0 and K % 16 == 0 else None
+        torch.cuda.synchronize()
+        if y is not None:
+            bad = (y.float() != K)
+            print(f"ones  M{M} K{K} N{N}: wrong={int(bad.sum())}/{y.numel()} sample={y[0, :4].tolist()} uniq={torch.unique(y.float())[:8].tolist()}")
+        # 2. random small ints (exact in fp8 and fp32)
+        g = torch.Generator(device=DEV).manual_seed(1)
+        ai = torch.randint(-3, 4, (M, K), device=DEV, generator=g).float()
+        bi = torch.randint(-3, 4, (N, K), device=DEV, generator=g).float()
+        a = ai.to(torch.float8_e4m3fn)
+        b = bi.to(torch.float8_e4m3fn).t()
+        y = ops.fp8_matmul(a, b, s_m, s_n, torch.float16, None)
+        ref = ai @ bi.t()
+        bad = (y.float() != ref)
+        print(f"ints  M{M} K{K} N{N}: wrong={int(bad.sum())}/{y.numel()}")
+        if bad.any():
+            rows = bad.any(dim=1).nonzero().flatten()[:16].tolist()
+            cols = bad.any(dim=0).nonzero().flatten()[:16].tolist()
+            print("   bad rows:", rows, " bad cols:", cols)
+            print("   got :", y[:4, :8].float().tolist())
+            print("   want:", ref[:4, :8].tolist())
+            # does y match ref with K truncated to the first 32 / 64 / 96 elements? (K-advance bug)
+            for kk in (32, 64, 96, 128):
+                if kk <= K:
+                    r2 = ai[:, :kk] @ bi[:, :kk].t()
+                    print(f"   match with K[:{kk}] only: {int((y.float() == r2).sum())}/{y.numel()}")
+        # int8
+        a8 = ai.to(torch.int8)
+        b8 = bi.to(torch.int8).t()
+        y = ops.int8_matmul(a8, b8, s_m, s_n, torch.float16, None, None, None)
+        bad = (y.float() != ref)
+        print(f"int8  M{M} K{K} N{N}: wrong={int(bad.sum())}/{y.numel()}")
+        if bad.any():
+            print("   got :", y[:4, :8].float().tolist())
+            print("   want:", ref[:4, :8].tolist())
+
+
+def gemm_perf():
+    print("== GEMM perf (TFLOP/s) ==")
+    res = {}
+    for (M, K, N) in ((8192, 3072, 9216), (512, 3072, 9216), (8192, 3072, 12288), (8192, 12288, 3072),
+                      (8704, 15360, 3072), (4608, 3072, 9216), (8192, 8192, 8192)):
+        g = torch.Generator(device=DEV).manual_seed(1)
+        a = torch.randn(M, K, device=DEV, generator=g).to(torch.float8_e4m3fn)
+        b = torch.randn(N, K, device=DEV, generator=g).to(torch.float8_e4m3fn).t()
+        sa = torch.rand(M, 1, device=DEV)
+        sb = torch.rand(N, 1, device=DEV)
+        bias = torch.randn(N, device=DEV).to(BF)
+        ms = timeit(lambda: ops.fp8_matmul(a, b, sa, sb, BF, bias))
+        tf = 2.0 * M * N * K / ms / 1e9
+        # cuBLASLt rowwise baseline (what the reference's torch backend runs on B200)
+        try:
+            ms_t = timeit(lambda: torch._scaled_mm(a, b, sa, sb.t(), bias, out_dtype=BF))
+            tf_t = 2.0 * M * N * K / ms_t / 1e9
+        except Exception as e:  # noqa: BLE001
+            ms_t, tf_t = float("nan"), float("nan")
+            print("   torch._scaled_mm failed:", str(e)[:200])
+        a8 = torch.randint(-128, 128, (M, K), device=DEV, generator=g).to(torch.int8)
+        b8 = torch.randint(-128, 128, (N, K), device=DEV, generator=g).to(torch.int8).t()
+        adj = torch.randint(-128, 127, (1, N), device=DEV).to(torch.int32)
+        azp = torch.randint(-128, 127, (M, 1), device=DEV).to(torch.int32)
+        ms8 = timeit(lambda: ops.int8_matmul(a8, b8, sa, sb, BF, adj, azp, bias))
+        tf8 = 2.0 * M * N * K / ms8 / 1e9
+        print(f"M{M} K{K} N{N}: fp8 {ms:.3f} ms {tf:.0f} TF | cublasLt fp8 {ms_t:.3f} ms {tf_t:.0f} TF | int8 {ms8:.3f} ms {tf8:.0f} TOP")
+        res[f"{M}x{K}x{N}"] = dict(fp8_ms=ms, fp8_tflops=tf, cublaslt_ms=ms_t, cublaslt_tflops=tf_t, int8_ms=ms8, int8_tops=tf8)
+    out["gemm_perf"] = res
+
+
+def elementwise_perf():
+    print("== elementwise perf (GB/s algorithmic) ==")
+    res = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+
+    def timed(fn, iters=10):
+        fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        for _ in range(iters):
+            flush.zero_()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / iters
+
+    for (M, K) in ((4608, 3072), (8704, 3072), (8704, 12288), (8704, 15360), (80640, 5120), (80640, 13824)):
+        x = torch.randn(M, K, device=DEV, dtype=BF)
+        ms = timed(lambda: ops.quantize_to_fp8(x))
+        gb = (3 * M * K + 4 * M) / ms / 1e6
+        ms8 = timed(lambda: ops.quantize_to_int8(x, False))
+        gb8 = (3 * M * K + 8 * M) / ms8 / 1e6
+        print(f"quant [{M},{K}]: fp8 {ms*1e3:.1f} us {gb:.0f} GB/s | int8 asym {ms8*1e3:.1f} us {gb8:.0f} GB/s")
+        res[f"quant_{M}x{K}"] = dict(fp8_us=ms * 1e3, fp8_gbs=gb, int8_us=ms8 * 1e3, int8_gbs=gb8)
+    for shape in ((1, 8704, 24, 128), (1, 80640, 5120), (2, 4685, 24, 64)):
+        x = torch.randn(*shape, device=DEV, dtype=BF)
+        w = torch.randn(shape[-1], device=DEV, dtype=BF)
+        ms = timed(lambda: ops.rms_norm(x, w, 1e-6))
+        gb = 4 * x.numel() / ms / 1e6
+        print(f"rms_norm {shape}: {ms*1e3:.1f} us {gb:.0f} GB/s")
+        res[f"rmsnorm_{'x'.join(map(str, shape))}"] = dict(us=ms * 1e3, gbs=gb)
+    for (S, d) in ((8704, 3072), (80640, 5120)):
+        q = torch.randn(1, S, d, device=DEV, dtype=BF)
+        k = torch.randn(1, S, d, device=DEV, dtype=BF)
+        cs = torch.rand(S, 128, device=DEV, dtype=BF)
+        ms = timed(lambda: ops.rotary_pos_embedding(q, k, 128, cs, False))
+        gb = (8 * S * d + 2 * S * 128) / ms / 1e6
+        print(f"rope [{S},{d}]: {ms*1e3:.1f} us {gb:.0f} GB/s")
+        res[f"rope_{S}x{d}"] = dict(us=ms * 1e3, gbs=gb)
+    for (M, d) in ((8192, 5120), (2048, 10240)):
+        x = torch.randn(M, 2 * d, device=DEV, dtype=BF)
+        ms = timed(lambda: ops.gelu_and_mul(x))
+        gb = 6 * M * d / ms / 1e6
+        print(f"gelu_and_mul [{M},{2*d}]: {ms*1e3:.1f} us {gb:.0f} GB/s")
+        res[f"gelumul_{M}x{d}"] = dict(us=ms * 1e3, gbs=gb)
+    out["elementwise_perf"] = res
+
+
+def op_overhead():
+    x = torch.randn(8, 64, device=DEV, dtype=BF)
+    t0 = time.perf_counter()
+    for _ in range(2000):
+        ops.quantize_to_fp8(x)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / 2000
+    print(f"host overhead per custom-op call (tiny quant): {dt*1e6:.1f} us")
+    out["custom_op_overhead_us"] = dt * 1e6
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["patterns", "gemm_perf", "elementwise_perf", "overhead"]
+    print(torch.cuda.get_device_name(0), torch.version.cuda)
+    if "patterns" in which:
+        gemm_patterns()
+    if "gemm_perf" in which:
+        gemm_perf()
+    if "elementwise_perf" in which:
+        elementwise_perf()
+    if "overhead" in which:
+        op_overhead()
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "diag.json"), "w") as f:
+        json.dump(out, f, indent=1)
