@@ -1,8 +1,501 @@
-// placeholder until the tcgen05 attention kernel lands (next commit)
-#include "common.cuh"
-extern "C" int fdm_attn_fwd(const void*, const void*, const void*, void*, const int8_t*, int64_t,
-                            int64_t, int64_t, int, int, int64_t, int64_t, int64_t, int64_t, int64_t,
-                            int64_t, int, int, float, int, void*) {
-  fdm::set_error("attention kernel not built yet");
-  return FDM_ERR_UNSUPPORTED;
+// Family 2: flash attention forward for B200 -- dense and block-sparse, non-causal MHA, bf16 / fp16
+// operands, token-major ("NHD") layouts with arbitrary token / batch strides (q, k, v may be
+// last-dim slices of a fused qkv projection).
+//
+// One CTA owns 256 query rows of one (batch, head): two 128-row Q tiles A and B that share every
+// K / V tile pulled through shared memory (halves L2->SMEM traffic per flop and lets one tile's
+// softmax overlap the other tile's MMAs):
+//
+//   warps 0-3 : softmax + correction + epilogue of Q tile A (thread <-> query row)
+//   warps 4-7 : same for Q tile B
+//   warp  8   : TMA producer -- Q tiles once, then K(t), V(t), K(t+1), ... through an NS-stage ring
+//               (128-byte swizzled [128 rows x 64 elements] boxes; OOB rows zero-filled)
+//   warp  9   : MMA issuer -- S_X = Q_X K^T (SS, K-major x K-major) into TMEM, then
+//               O_X += P_X V (TS: P read from TMEM where the softmax warps wrote it over S_X,
+//               V consumed MN-major straight from its row-major tile -- no transpose anywhere)
+//
+//   TMEM columns: S_A [0,128) | S_B [128,256) | O_A [256,256+HD) | O_B [384,384+HD)
+//
+// Softmax is the usual online form in the exp2 domain with lazy rescaling: the running max only
+// moves (and O is only rescaled through TMEM) when it grows by more than 2^8, so the correction
+// is off the critical path for all but the first tiles.
+//
+// Block-sparse ("Sparge" / radial masks, fastdm/sparse/xsparse.py): an int8 mask
+// [B, H, ceil(Sq/bq), ceil(Sk/bk)] (bq, bk in {64,128}); KV tiles whose mask entries are all zero
+// for this CTA are skipped by all three roles (no TMA, no MMA, no softmax); partially masked tiles
+// get -inf on the masked 64-column segments. Masked-out keys are excluded from the softmax.
+//
+// Semantics: fastdm/kernel/torch/attention.py:7-43 (F.scaled_dot_product_attention, non-causal),
+// checked against the fp32 reference of tests/test_attention.py:23-63 at atol 1.8e-2 (:94).
+// Replaces the library routes of fastdm/kernel/cuda/attention.py:149-261.
+#include "sm100.cuh"
+
+namespace fdm {
+using namespace sm100;
+
+constexpr int kAttnThreads = 320;
+constexpr int kQTile = 128;   // rows per Q tile (UMMA M)
+constexpr int kKvTile = 128;  // keys per KV tile (UMMA N of QK^T, K extent of PV)
+constexpr int kMaxKvTiles = 8192;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+template <int HD>
+struct AttnSmem {
+  static constexpr int kHalves = HD / 64;              // 64-element (128 B) column groups per row
+  static constexpr int kTileBytes = kKvTile * HD * 2;  // one Q / K / V tile
+  static constexpr int kStages = HD == 128 ? 4 : 6;
+  static constexpr int kQOff = 0;
+  static constexpr int kKvOff = 2 * kTileBytes;
+  static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
+  static constexpr int kNumBars = 1 + 2 * kStages + 6;
+  static constexpr int kFlagsOff = kBarOff + kNumBars * 8 + 16;
+  static constexpr int kTotal = kFlagsOff + kMaxKvTiles + 1024;
+};
+
+struct AttnParams {
+  void* o;
+  const int8_t* mask;
+  int B, H, Sq, Sk;
+  int n_kv_tiles;
+  int mask_bq, mask_bk, nbq, nbk;
+  float scale_log2;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool F16>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+}
+
+template <int HD, bool F16>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using S = AttnSmem<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const uint32_t bar_base = base + S::kBarOff;
+  const uint32_t q_full = bar_base;
+  auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bar_base + 8u * (1 + S::kStages + s); };
+  auto s_full = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + x); };
+  auto p_ready = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 2 + x); };
+  auto o_done = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 4 + x); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S::kBarOff + S::kNumBars * 8);
+  uint8_t* flags = smem + S::kFlagsOff;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * kQTile;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const bool has_mask = p.mask != nullptr;
+  const int8_t* mask_bh = has_mask ? p.mask + ((int64_t)b * p.H + h) * p.nbq * p.nbk : nullptr;
+
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(kv_full(s), 1);
+      mbar_init(kv_empty(s), 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(s_full(x), 1);
+      mbar_init(p_ready(x), 128);
+      mbar_init(o_done(x), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<1>(smem_u32(tmem_ptr_smem), 512);
+  if (has_mask) {
+    // which KV tiles does this CTA need at all? (identical answer for all three roles)
+    const int qb_lo = q0 / p.mask_bq;
+    const int qb_hi = min((min(q0 + 2 * kQTile, p.Sq) - 1) / p.mask_bq, p.nbq - 1);
+    for (int j = threadIdx.x; j < p.n_kv_tiles; j += kAttnThreads) {
+      const int kb_lo = (j * kKvTile) / p.mask_bk;
+      const int kb_hi = min((min((j + 1) * kKvTile, p.Sk) - 1) / p.mask_bk, p.nbk - 1);
+      int any = 0;
+      for (int qb = qb_lo; qb <= qb_hi; ++qb)
+        for (int kb = kb_lo; kb <= kb_hi; ++kb) any |= mask_bh[(int64_t)qb * p.nbk + kb];
+      flags[j] = any ? 1 : 0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  auto tile_active = [&](int j) -> bool { return !has_mask || flags[j] != 0; };
+
+  constexpr uint32_t kFmt = F16 ? kFmtF16 : kFmtBF16;
+  constexpr uint32_t kIdescQK = make_idesc(kFmt, kFmt, kAccF32, kQTile, kKvTile, 0, 0);
+  constexpr uint32_t kIdescPV = make_idesc(kFmt, kFmt, kAccF32, kQTile, HD, 0, 1);
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * S::kTileBytes);
+#pragma unroll
+      for (int x = 0; x < 2; ++x)
+#pragma unroll
+        for (int hf = 0; hf < S::kHalves; ++hf)
+          tma_load_4d(base + S::kQOff + x * S::kTileBytes + hf * (kQTile * 128), &tmap_q, q_full,
+                      hf * 64, h, q0 + x * kQTile, b);
+      uint32_t u = 0;
+      for (int j = 0; j < p.n_kv_tiles; ++j) {
+        if (!tile_active(j)) continue;
+#pragma unroll
+        for (int kv = 0; kv < 2; ++kv) {
+          const int stage = u % S::kStages;
+          const uint32_t parity = ((u / S::kStages) & 1u) ^ 1u;
+          mbar_wait(kv_empty(stage), parity);
+          mbar_arrive_expect_tx(kv_full(stage), S::kTileBytes);
+          const uint32_t dst = base + S::kKvOff + stage * S::kTileBytes;
+#pragma unroll
+          for (int hf = 0; hf < S::kHalves; ++hf)
+            tma_load_4d(dst + hf * (kKvTile * 128), kv == 0 ? &tmap_k : &tmap_v, kv_full(stage),
+                        hf * 64, h, j * kKvTile, b);
+          ++u;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
+      const uint32_t tO[2] = {tmem_base + 256u, tmem_base + 384u};
+      const uint32_t q_smem[2] = {base + S::kQOff, base + S::kQOff + S::kTileBytes};
+      auto issue_qk = [&](int x, uint32_t k_smem) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks) {
+          const uint32_t off = (uint32_t)(ks / 4) * (kQTile * 128) + (uint32_t)(ks % 4) * 32u;
+          umma_ss<MmaKind::F16, 1>(tS[x], make_desc_kmajor_sw128(q_smem[x] + off),
+                                   make_desc_kmajor_sw128(k_smem + off), kIdescQK, ks != 0);
+        }
+      };
+      auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate) {
+#pragma unroll
+        for (int ks = 0; ks < kKvTile / 16; ++ks) {
+          // 16 keys = 16 rows of 128 B; P: 16 bf16 = 8 TMEM columns
+          const uint64_t bdesc = make_desc_mnmajor_sw128(v_smem + (uint32_t)ks * 2048u, kKvTile * 128, 1024);
+          umma_ts<MmaKind::F16>(tO[x], tS[x] + (uint32_t)ks * 8u, bdesc, kIdescPV,
+                                (accumulate || ks != 0) ? 1u : 0u);
+        }
+      };
+      auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kTileBytes; };
+      auto wait_full = [&](uint32_t u) {
+        mbar_wait(kv_full(u % S::kStages), (u / S::kStages) & 1u);
+        tc_fence_after();
+      };
+
+      // active tiles are numbered t = 0,1,...; K(t) is ring slot 2t, V(t) is ring slot 2t+1
+      int j = 0;
+      while (j < p.n_kv_tiles && !tile_active(j)) ++j;
+      if (j < p.n_kv_tiles) {
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        wait_full(0);
+        issue_qk(0, stage_addr(0));
+        tc_commit(s_full(0));
+        issue_qk(1, stage_addr(0));
+        tc_commit(s_full(1));
+        tc_commit(kv_empty(0));
+        uint32_t t = 0;
+        while (true) {
+          int jn = j + 1;
+          while (jn < p.n_kv_tiles && !tile_active(jn)) ++jn;
+          const bool has_next = jn < p.n_kv_tiles;
+          const uint32_t uV = 2 * t + 1, uKn = 2 * t + 2;
+          const uint32_t ph = t & 1u;
+          wait_full(uV);
+          mbar_wait(p_ready(0), ph);
+          tc_fence_after();
+          issue_pv(0, stage_addr(uV), t != 0);
+          tc_commit(o_done(0));
+          if (has_next) {
+            wait_full(uKn);
+            issue_qk(0, stage_addr(uKn));
+            tc_commit(s_full(0));
+          }
+          mbar_wait(p_ready(1), ph);
+          tc_fence_after();
+          issue_pv(1, stage_addr(uV), t != 0);
+          tc_commit(o_done(1));
+          tc_commit(kv_empty(uV % S::kStages));
+          if (!has_next) break;
+          issue_qk(1, stage_addr(uKn));
+          tc_commit(s_full(1));
+          tc_commit(kv_empty(uKn % S::kStages));
+          j = jn;
+          ++t;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int x = warp >> 2;              // Q tile of this warpgroup
+    const int lane_group = warp & 3;      // TMEM lanes [32*lane_group, +32)
+    const int row_in_tile = lane_group * 32 + lane;
+    const int row = q0 + x * kQTile + row_in_tile;  // global query index
+    const uint32_t lane_off = (uint32_t)(lane_group * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + (uint32_t)(x * 128);
+    const uint32_t tO = tmem_base + lane_off + 256u + (uint32_t)(x * 128);
+    const int8_t* mask_row = nullptr;
+    if (has_mask) mask_row = mask_bh + (int64_t)min(row / p.mask_bq, p.nbq - 1) * p.nbk;
+
+    float m_run = -INFINITY;  // running max, scaled-log2 domain
+    float l_run = 0.f;
+    uint32_t t = 0;
+    for (int j = 0; j < p.n_kv_tiles; ++j) {
+      if (!tile_active(j)) continue;
+      mbar_wait(s_full(x), t & 1u);
+      tc_fence_after();
+      const int valid = p.Sk - j * kKvTile;  // keys of this tile inside the sequence
+      bool seg0 = true, seg1 = true;
+      if (has_mask) {
+        const int kb0 = min((j * kKvTile) / p.mask_bk, p.nbk - 1);
+        const int kb1 = min((j * kKvTile + 64) / p.mask_bk, p.nbk - 1);
+        seg0 = mask_row[kb0] != 0;
+        seg1 = mask_row[kb1] != 0;
+      }
+      const bool masked_tile = valid < kKvTile || has_mask;
+      // -inf on keys beyond the sequence end and on masked 64-key segments
+      auto apply_mask = [&](uint32_t(&r)[32], int c) {
+        if (masked_tile) {
+          const bool seg = c < 2 ? seg0 : seg1;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = (seg && (c * 32 + i) < valid) ? r[i] : 0xff800000u;
+        }
+      };
+
+      // ---- pass 1: row max (S is read from TMEM twice; a 128-register row would spill) ----
+      float mx = -INFINITY;
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tS, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 32u, rb);
+        apply_mask(ra, 0);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 64u, ra);
+        apply_mask(rb, 1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 96u, rb);
+        apply_mask(ra, 2);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
+        tmem_ld_wait();
+        apply_mask(rb, 3);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const bool need = m_new > m_run + kRescaleThreshold;  // first finite max always triggers
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_next = need ? m_new : m_run;
+        const float alpha = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_next);
+        l_run *= alpha;
+        m_run = m_next;
+        if (t > 0) {
+          // O_X may only be touched between PV_X(t-1) and PV_X(t)
+          mbar_wait(o_done(x), (t - 1) & 1u);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld_32x32(tO + (uint32_t)(c * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_32x32(tO + (uint32_t)(c * 32), r);
+          }
+        }
+      }
+      // ---- pass 2: P = exp2(S*scale - m), packed 2 per column over S_X's own columns:
+      //      chunk c (S columns [32c, 32c+32)) becomes P columns [16c, 16c+16), already consumed ----
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      float sum = 0.f;
+      auto emit = [&](uint32_t(&r)[32], int c) {
+        apply_mask(r, c);
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
+          const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+          sum += p0 + p1;
+          pk[i] = pack2<F16>(p0, p1);
+        }
+        tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
+      };
+      {
+        uint32_t ra[32], rb[32];
+        tmem_ld_32x32(tS, ra);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 32u, rb);
+        emit(ra, 0);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 64u, ra);
+        emit(rb, 1);
+        tmem_ld_wait();
+        tmem_ld_32x32(tS + 96u, rb);
+        emit(ra, 2);
+        tmem_ld_wait();
+        emit(rb, 3);
+      }
+      l_run += sum;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_ready(x));
+      ++t;
+    }
+
+    // ---- epilogue: O / l -> global ----
+    const bool row_ok = row < p.Sq;
+    uint16_t* out_row = reinterpret_cast<uint16_t*>(p.o) + (((int64_t)b * p.Sq + row) * p.H + h) * HD;
+    if (t > 0) {
+      mbar_wait(o_done(x), (t - 1) & 1u);
+      tc_fence_after();
+    }
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t r[32];
+      if (t > 0) {
+        tmem_ld_32x32(tO + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          U128 o;
+          o.x = pack2<F16>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
+          o.y = pack2<F16>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
+          o.z = pack2<F16>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
+          o.w = pack2<F16>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
+          stg128(out_row + c * 32 + q * 8, o);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, 512);
+  }
+}
+
+template <int HD, bool F16>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p, cudaStream_t st) {
+  using S = AttnSmem<HD>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  FDM_CUDA(cudaGetDevice(&dev));
+  if (!attr_set[dev]) {
+    FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  S::kTotal));
+    attr_set[dev] = true;
+  }
+  dim3 grid((unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile)), (unsigned)p.H, (unsigned)p.B);
+  attn_fwd_kernel<HD, F16><<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  FDM_LAUNCH_CHECK("attn_fwd kernel launch");
+  return FDM_OK;
+}
+
+static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,
+                         int64_t batch_stride, int64_t token_stride) {
+  // dims innermost first: d, head, token, batch
+  uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)token_stride * 2, (uint64_t)batch_stride * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, ptr, dims, strides, box,
+                   CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace fdm
+
+using namespace fdm;
+
+extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o,
+                            const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
+                            int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
+                            int64_t v_ts, int mask_bq, int mask_bk, float scale, int qkv_dtype,
+                            void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(B >= 0 && Sq >= 0 && Sk >= 0 && H > 0, "attn: bad shape");
+  if (B == 0 || Sq == 0) return FDM_OK;
+  FDM_REQUIRE(q && k && v && o, "attn: null pointer");
+  FDM_REQUIRE(hd == 64 || hd == 128, "attn: head_dim %d unsupported (64 or 128)", hd);
+  if (qkv_dtype == FDM_E4M3) {
+    set_error("attn: fp8 q/k/v is not built in this version");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  FDM_REQUIRE(qkv_dtype == FDM_BF16 || qkv_dtype == FDM_F16, "attn: q/k/v dtype must be bf16 or f16");
+  FDM_REQUIRE(scale > 0.f, "attn: scale must be positive");
+  FDM_REQUIRE(Sk > 0, "attn: empty key sequence");
+  FDM_REQUIRE(Sq < (1LL << 31) && Sk <= (int64_t)kMaxKvTiles * kKvTile && H < 65536 && B < 65536,
+              "attn: sequence too long (Sk <= %d)", kMaxKvTiles * kKvTile);
+  for (int64_t s : {q_ts, k_ts, v_ts, q_bs, k_bs, v_bs})
+    FDM_REQUIRE(s % 8 == 0, "attn: strides must be multiples of 8 elements (16 bytes)");
+  FDM_REQUIRE((uintptr_t)q % 16 == 0 && (uintptr_t)k % 16 == 0 && (uintptr_t)v % 16 == 0 &&
+                  (uintptr_t)o % 16 == 0,
+              "attn: pointers must be 16-byte aligned");
+  FDM_REQUIRE(q_ts >= (int64_t)H * hd && k_ts >= (int64_t)H * hd && v_ts >= (int64_t)H * hd,
+              "attn: token stride smaller than H*hd");
+  AttnParams p;
+  p.o = o;
+  p.mask = block_mask;
+  p.B = (int)B;
+  p.H = H;
+  p.Sq = (int)Sq;
+  p.Sk = (int)Sk;
+  p.n_kv_tiles = (int)((Sk + kKvTile - 1) / kKvTile);
+  p.mask_bq = mask_bq;
+  p.mask_bk = mask_bk;
+  p.nbq = p.nbk = 0;
+  if (block_mask) {
+    FDM_REQUIRE((mask_bq == 64 || mask_bq == 128) && (mask_bk == 64 || mask_bk == 128),
+                "attn: mask block sizes must be 64 or 128");
+    p.nbq = (int)((Sq + mask_bq - 1) / mask_bq);
+    p.nbk = (int)((Sk + mask_bk - 1) / mask_bk);
+  }
+  p.scale_log2 = scale * 1.4426950408889634f;
+  CUtensorMap tq, tk, tv;
+  // batch stride of a single-batch tensor is irrelevant but must still be a legal stride
+  if (B == 1) {
+    q_bs = Sq * q_ts;
+    k_bs = Sk * k_ts;
+    v_bs = Sk * v_ts;
+  }
+  rc = make_qkv_tmap(&tq, q, B, Sq, H, hd, q_bs, q_ts);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&tk, k, B, Sk, H, hd, k_bs, k_ts);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&tv, v, B, Sk, H, hd, v_bs, v_ts);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f16 = qkv_dtype == FDM_F16;
+  if (hd == 128) return f16 ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
+  return f16 ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
 }

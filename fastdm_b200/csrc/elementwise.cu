@@ -108,10 +108,13 @@ __device__ __forceinline__ QParams make_qparams(float mn, float mx, float amax_f
 template <int MODE>
 __device__ __forceinline__ float qtransform(float x, const QParams& p) {
   float q = __fdiv_rn(x, p.scale);
-  if (MODE == 0) return fminf(fmaxf(q, -448.0f), 448.0f);
+  if (MODE == 0) {
+    // torch.clamp propagates NaN (0/0 rows with a zero scale); cvt.satfinite keeps it as e4m3 NaN
+    return (q != q) ? q : fminf(fmaxf(q, -448.0f), 448.0f);
+  }
   if (MODE == 2) q = __fadd_rn(q, p.zpf);
-  q = rintf(q);
-  return fminf(fmaxf(q, -128.0f), 127.0f);
+  const float r = fminf(fmaxf(rintf(q), -128.0f), 127.0f);
+  return (q != q) ? 0.0f : r;  // torch: NaN.to(int8) == 0
 }
 
 __device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {
@@ -119,9 +122,11 @@ __device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d
          ((uint32_t)((int)c & 0xff) << 16) | ((uint32_t)((int)d & 0xff) << 24);
 }
 
-// One CTA per row, the row lives in registers: VPT 16-byte vectors per thread.
+// One CTA per row, the row lives in registers as raw 16-byte vectors (VPT per thread): one HBM
+// read, one write. Keeping the packed bits (4 regs / vector) instead of 8 floats lets ~1.3k threads
+// stay resident per SM, i.e. > 80 KB of loads in flight per SM.
 template <typename T, int MODE, int ACT, int VPT>
-__global__ void __launch_bounds__(256) quant_row_kernel(const T* __restrict__ in,
+__global__ void __launch_bounds__(512) quant_row_kernel(const T* __restrict__ in,
                                                         uint8_t* __restrict__ out,
                                                         float* __restrict__ scale,
                                                         int32_t* __restrict__ azp, int cols,
@@ -130,20 +135,27 @@ __global__ void __launch_bounds__(256) quant_row_kernel(const T* __restrict__ in
   const int64_t row = blockIdx.x;
   const int nvec = cols >> 3;
   const T* src = in + row * in_row_stride;
-  float f[VPT][8];
+  U128 raw[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) raw[i] = ldg128_stream(src + (int64_t)v * 8);
+  }
   float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
-      U128 raw = ldg128_stream(src + (int64_t)v * 8);
-      unpack8<T>(raw, f[i]);
+      float f[8];
+      unpack8<T>(raw[i], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        f[i][j] = apply_act<ACT, T>(f[i][j]);
-        mn = fminf(mn, f[i][j]);
-        mx = fmaxf(mx, f[i][j]);
+        f[j] = apply_act<ACT, T>(f[j]);
+        mn = fminf(mn, f[j]);
+        mx = fmaxf(mx, f[j]);
       }
+      // keep the activated (T-rounded) values so the transcendental is evaluated once
+      if (ACT != FDM_ACT_NONE) raw[i] = pack8<T>(f);
     }
   }
   MinMax r = block_minmax(mn, mx, red);
@@ -157,9 +169,10 @@ __global__ void __launch_bounds__(256) quant_row_kernel(const T* __restrict__ in
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
-      float q[8];
+      float f[8], q[8];
+      unpack8<T>(raw[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = qtransform<MODE>(f[i][j], p);
+      for (int j = 0; j < 8; ++j) q[j] = qtransform<MODE>(f[j], p);
       uint32_t lo, hi;
       if (MODE == 0) {
         lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
@@ -214,7 +227,7 @@ static int launch_quant_t(const void* in, void* out, float* scale, int32_t* azp,
   const T* src = (const T*)in;
   uint8_t* dst = (uint8_t*)out;
   const bool vec_ok = sizeof(T) == 2 && (cols % 8 == 0) && (stride % 8 == 0) &&
-                      ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 8 == 0) && cols <= 8 * 256 * 8;
+                      ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 8 == 0) && cols <= 8 * 512 * 8;
   if (!vec_ok) {
     quant_row_generic_kernel<T, MODE, ACT><<<(unsigned)rows, 256, 0, st>>>(src, dst, scale, azp,
                                                                            cols, stride);
@@ -222,8 +235,9 @@ static int launch_quant_t(const void* in, void* out, float* scale, int32_t* azp,
   }
   if constexpr (sizeof(T) == 2) {
     const int nvec = (int)(cols / 8);
-    int block = ((nvec + 31) / 32) * 32;
-    if (block > 256) block = 256;
+    // aim for 4 vectors (64 B) per thread; rows longer than 512*4 vectors fall back to 8 / thread
+    int block = (((nvec + 3) / 4 + 31) / 32) * 32;
+    if (block > 512) block = 512;
     const int vpt = (nvec + block - 1) / block;
     const unsigned g = (unsigned)rows;
     if (vpt <= 1)

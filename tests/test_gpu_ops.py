@@ -324,3 +324,129 @@ def test_matmul_argument_checks(ops):
         ops.fp8_matmul(a, b, torch.ones(15, 1, device=DEV), s1, BF, None)
     y = ops.fp8_matmul(a, b, s1, s1, BF, None)
     assert y.shape == (16, 16) and float(y.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ attention
+ATOL_ATTN = 1.8e-2  # tests/test_attention.py:94 (rtol 0) against the fp32 reference
+
+
+def attn_oracle(q, k, v, h, hd, scale, mask=None, bq=128, bk=64):
+    b, sq, sk = q.shape[0], q.shape[1], k.shape[1]
+    o = R.attention_ref(q.view(b, sq, h, hd), k.view(b, sk, h, hd), v.view(b, sk, h, hd), scale, mask, bq, bk)
+    return o.reshape(b, sq, h * hd)
+
+
+def test_attention_golden(ops):
+    for c in golden("attention.pt"):
+        y = ops.scaled_dot_product_attention(c["q"].to(DEV), c["k"].to(DEV), c["v"].to(DEV), c["h"], c["h"], c["hd"],
+                                             scale=c["scale"])
+        assert y.shape == c["y"].shape and y.dtype == BF
+        err = (y.cpu().float() - c["y"].float()).abs().max().item()
+        assert err <= ATOL_ATTN, f"max abs err {err} for q{tuple(c['q'].shape)} k{tuple(c['k'].shape)}"
+
+
+# tests/test_attention.py:7-21 (all nine cases)
+ATTN_CASES = [(1, 4608, 4608, 24, 128), (1, 4110, 4110, 24, 128), (2, 4096, 4096, 10, 64), (2, 4096, 77, 10, 64),
+              (2, 1024, 1024, 20, 64), (2, 1024, 77, 20, 64), (1, 4106, 4106, 24, 128), (2, 4685, 4685, 24, 64),
+              (2, 4096, 4096, 24, 64)]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES)
+def test_attention_vs_fp32_reference(ops, case):
+    b, sq, sk, h, hd = case
+    torch.manual_seed(0)  # tests/test_attention.py:69
+    q = torch.randn(b, sq, h * hd, device=DEV).to(BF)
+    k = torch.randn(b, sk, h * hd, device=DEV).to(BF)
+    v = torch.randn(b, sk, h * hd, device=DEV).to(BF)
+    scale = 1.0 / hd ** 0.5
+    y = ops.scaled_dot_product_attention(q, k, v, h, h, hd, scale=scale)
+    # fp32 reference evaluated on the GPU in fp32 (same formula as oracle/ops_ref.attention_ref), head by head
+    qf = q.view(b, sq, h, hd).transpose(1, 2).float()
+    kf = k.view(b, sk, h, hd).transpose(1, 2).float()
+    vf = v.view(b, sk, h, hd).transpose(1, 2).float()
+    worst = 0.0
+    for hh in range(h):
+        s_ = torch.matmul(qf[:, hh], kf[:, hh].transpose(-1, -2)) * scale
+        o_ = torch.matmul(torch.softmax(s_, dim=-1), vf[:, hh]).to(BF)
+        worst = max(worst, (y.view(b, sq, h, hd)[:, :, hh].float() - o_.float()).abs().max().item())
+    assert worst <= ATOL_ATTN, f"max abs err {worst}"
+    # and a slice of it against the CPU oracle proper
+    rows = slice(sq - 130, sq)
+    ref = attn_oracle(q[:1, rows].cpu(), k[:1].cpu(), v[:1].cpu(), h, hd, scale)
+    assert (y[:1, rows].cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
+
+
+def test_attention_strided_views_of_fused_qkv(ops):
+    # value is a last-dim slice of the fused qkv projection: layer/transformer.py:269,300
+    torch.manual_seed(1)
+    b, s, h, hd = 1, 700, 24, 128
+    fused = torch.randn(b, s, 3 * h * hd, device=DEV).to(BF)
+    q, k, v = fused[:, :, : h * hd], fused[:, :, h * hd: 2 * h * hd], fused[:, :, 2 * h * hd:]
+    y = ops.scaled_dot_product_attention(q, k, v, h, h, hd)
+    y2 = ops.scaled_dot_product_attention(q.contiguous(), k.contiguous(), v.contiguous(), h, h, hd)
+    assert torch.equal(y, y2)
+    ref = attn_oracle(q.cpu().contiguous(), k.cpu().contiguous(), v.cpu().contiguous(), h, hd, hd ** -0.5)
+    assert (y.cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
+
+
+@pytest.mark.parametrize("geom", [(128, 64), (64, 128), (128, 128), (64, 64)])
+@pytest.mark.parametrize("shape", [(1, 900, 900, 3, 128), (2, 333, 515, 2, 64)])
+def test_sparse_attention_random_block_masks(ops, geom, shape):
+    bq, bk = geom
+    b, sq, sk, h, hd = shape
+    g = torch.Generator().manual_seed(bq + bk + sq)
+    q = torch.randn(b, sq, h * hd, generator=g).to(BF)
+    k = torch.randn(b, sk, h * hd, generator=g).to(BF)
+    v = torch.randn(b, sk, h * hd, generator=g).to(BF)
+    nbq, nbk = -(-sq // bq), -(-sk // bk)
+    mask = (torch.rand(b, h, nbq, nbk, generator=g) < 0.5).to(torch.int8)
+    mask[:, :, 0, :] = 0          # a fully masked query block -> zeros
+    mask[:, :, -1, :] = 1         # a dense one
+    if nbq > 2:
+        mask[:, :, 1, :] = 0
+        mask[:, :, 1, -1] = 1     # only the ragged last key block
+    y = ops.sparse_scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), h, h, hd, scale=hd ** -0.5,
+                                                sparse_mask=mask.to(DEV), block_q=bq, block_k=bk)
+    ref = attn_oracle(q, k, v, h, hd, hd ** -0.5, mask, bq, bk)
+    assert (y.cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
+    assert float(y[:, : min(bq, sq)].abs().max()) == 0.0
+
+
+def test_sparse_attention_all_ones_equals_dense(ops):
+    # the reference's only sparse test: tests/test_sparge_attention.py:81 (mask = ones)
+    torch.manual_seed(0)
+    b, s, h, hd = 1, 2000, 4, 128
+    q, k, v = (torch.randn(b, s, h * hd, device=DEV).to(BF) for _ in range(3))
+    mask = torch.ones(b, h, -(-s // 128), -(-s // 64), dtype=torch.int8, device=DEV)
+    y = ops.sparse_scaled_dot_product_attention(q, k, v, h, h, hd, sparse_mask=mask)
+    assert torch.equal(y, ops.scaled_dot_product_attention(q, k, v, h, h, hd))
+
+
+def test_attention_constant_value_property_full_size(ops):
+    # size-independent property at the Wan2.2 shape (N = 80 640, 128-d heads; 2 of the 40 heads):
+    # with V constant along the sequence the output equals that constant row whatever the softmax did
+    s, h, hd = 80640, 2, 128
+    g = torch.Generator(device=DEV).manual_seed(2)
+    q = torch.randn(1, s, h * hd, device=DEV, generator=g).to(BF)
+    k = torch.randn(1, s, h * hd, device=DEV, generator=g).to(BF)
+    vrow = torch.randn(1, 1, h * hd, device=DEV, generator=g).to(BF)
+    v = vrow.expand(1, s, h * hd).contiguous()
+    y = ops.scaled_dot_product_attention(q, k, v, h, h, hd)
+    assert (y.float() - vrow.float()).abs().max().item() <= 2e-2 * float(vrow.float().abs().max())
+    # cross attention 80640 x 512 (Wan attn2) against the oracle on a row sample
+    k2 = torch.randn(1, 512, h * hd, device=DEV, generator=g).to(BF)
+    v2 = torch.randn(1, 512, h * hd, device=DEV, generator=g).to(BF)
+    y2 = ops.scaled_dot_product_attention(q, k2, v2, h, h, hd)
+    rows = slice(80640 - 300, 80640)
+    ref = attn_oracle(q[:, rows].cpu(), k2.cpu(), v2.cpu(), h, hd, hd ** -0.5)
+    assert (y2[:, rows].cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
+
+
+def test_attention_argument_checks(ops):
+    q = torch.zeros(1, 8, 256, device=DEV, dtype=BF)
+    with pytest.raises(NotImplementedError):
+        ops.scaled_dot_product_attention(q, q, q, 2, 2, 128, is_causal=True)
+    with pytest.raises(RuntimeError):
+        ops.scaled_dot_product_attention(q, q, q, 3, 3, 128)
+    with pytest.raises(RuntimeError):
+        ops.scaled_dot_product_attention(q, q, q, 8, 8, 32)  # head_dim 32 unsupported

@@ -158,6 +158,70 @@ def elementwise_perf():
     out["elementwise_perf"] = res
 
 
+def attn_perf():
+    print("== attention perf (TFLOP/s) ==")
+    res = {}
+    for (b, sq, sk, h, hd) in ((1, 4608, 4608, 24, 128), (1, 8704, 8704, 24, 128), (2, 4685, 4685, 24, 64),
+                               (1, 80640, 80640, 4, 128), (1, 80640, 512, 40, 128)):
+        q = torch.randn(b, sq, h * hd, device=DEV, dtype=BF)
+        k = torch.randn(b, sk, h * hd, device=DEV, dtype=BF)
+        v = torch.randn(b, sk, h * hd, device=DEV, dtype=BF)
+        ms = timeit(lambda: ops.scaled_dot_product_attention(q, k, v, h, h, hd), iters=5, warm=2)
+        fl = 4.0 * b * h * sq * sk * hd
+        qt, kt, vt = (t.view(b, -1, h, hd).transpose(1, 2) for t in (q, k, v))
+        try:
+            ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), iters=5, warm=2)
+        except Exception as e:  # noqa: BLE001
+            ms_t = float("nan")
+            print("   torch sdpa failed:", str(e)[:200])
+        print(f"attn b{b} sq{sq} sk{sk} h{h} hd{hd}: {ms:.3f} ms {fl/ms/1e9:.0f} TF | torch sdpa {ms_t:.3f} ms {fl/ms_t/1e9:.0f} TF")
+        res[f"{b}x{sq}x{sk}x{h}x{hd}"] = dict(ms=ms, tflops=fl / ms / 1e9, torch_ms=ms_t, torch_tflops=fl / ms_t / 1e9)
+    out["attn_perf"] = res
+
+
+def attn_patterns():
+    print("== attention structured checks ==")
+    import math
+    for (b, sq, sk, h, hd) in ((1, 128, 128, 1, 128), (1, 256, 128, 1, 128), (1, 256, 256, 1, 128), (1, 256, 384, 2, 64),
+                               (1, 300, 200, 2, 128)):
+        torch.manual_seed(0)
+        q = torch.randn(b, sq, h * hd, device=DEV).to(BF)
+        k = torch.randn(b, sk, h * hd, device=DEV).to(BF)
+        v = torch.randn(b, sk, h * hd, device=DEV).to(BF)
+        y = ops.scaled_dot_product_attention(q, k, v, h, h, hd)
+        torch.cuda.synchronize()
+        qf, kf, vf = (t.view(b, -1, h, hd).transpose(1, 2).float() for t in (q, k, v))
+        ref = torch.softmax(qf @ kf.transpose(-1, -2) / math.sqrt(hd), -1) @ vf
+        ref = ref.transpose(1, 2).reshape(b, sq, h * hd)
+        err = (y.float() - ref).abs()
+        print(f"attn b{b} sq{sq} sk{sk} h{h} hd{hd}: max err {err.max().item():.4f} mean {err.mean().item():.5f} nan={int(torch.isnan(y.float()).sum())}")
+        if err.max().item() > 0.02:
+            # which rows / columns are off?  and: uniform-attention hypothesis (P layout wrong -> garbage)
+            bad_rows = (err.amax(dim=2) > 0.02)[0].nonzero().flatten()
+            print("   bad rows:", bad_rows[:10].tolist(), "... count", len(bad_rows))
+            bad_cols = (err.amax(dim=1) > 0.02)[0].nonzero().flatten()
+            print("   bad cols:", bad_cols[:10].tolist(), "... count", len(bad_cols))
+            print("   got :", y[0, 0, :8].float().tolist())
+            print("   want:", ref[0, 0, :8].tolist())
+            # V constant test isolates QK/softmax from PV layout
+            vc = v[:, :1].expand_as(v).contiguous()
+            yc = ops.scaled_dot_product_attention(q, k, vc, h, h, hd)
+            print("   const-V err:", (yc.float() - vc[:, :1].float()).abs().max().item())
+            # one-hot attention (huge scale on identical q/k rows) isolates P/V ordering
+            if sq == sk:
+                q1 = torch.zeros_like(q)
+                k1 = torch.zeros_like(k)
+                eye = torch.eye(hd, device=DEV)
+                for hh in range(h):
+                    idx = torch.arange(sq, device=DEV) % hd
+                    q1[0, :, hh * hd:(hh + 1) * hd] = eye[idx] * 30
+                    k1[0, :, hh * hd:(hh + 1) * hd] = eye[idx] * 30
+                y1 = ops.scaled_dot_product_attention(q1, k1, v, h, h, hd)
+                r1 = torch.softmax(q1.view(b, sq, h, hd).transpose(1, 2).float() @ k1.view(b, sk, h, hd).transpose(1, 2).float().transpose(-1, -2) / math.sqrt(hd), -1) @ vf
+                r1 = r1.transpose(1, 2).reshape(b, sq, h * hd)
+                print("   periodic-onehot err:", (y1.float() - r1).abs().max().item())
+
+
 def op_overhead():
     x = torch.randn(8, 64, device=DEV, dtype=BF)
     t0 = time.perf_counter()
@@ -178,6 +242,10 @@ if __name__ == "__main__":
         gemm_perf()
     if "elementwise_perf" in which:
         elementwise_perf()
+    if "attn_patterns" in which:
+        attn_patterns()
+    if "attn_perf" in which:
+        attn_perf()
     if "overhead" in which:
         op_overhead()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
