@@ -28,10 +28,21 @@ SIGNATURES = {
                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "fdm_gemm_int8": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "fdm_gemm_fp8_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
+                                      c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
+    "fdm_gemm_int8_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int, c_int,
+                                       c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "fdm_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                              c_int64, c_int64, c_int64, c_int, c_int,
-                             c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
+                             c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                              c_int, c_int, c_float, c_int, c_void_p]),
+    "fdm_qk_norm_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
+                                 c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_int, c_void_p]),
+    "fdm_layernorm_modulate_quant": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_int64, c_int64, c_int64, c_int64, c_int64, c_float,
+                                             c_int, c_int, c_int, c_void_p]),
     "fdm_ulysses_pack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p]),
     "fdm_ulysses_unpack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p]),
 }

@@ -1,0 +1,243 @@
+"""DiT transformer blocks on the fused B200 kernels -- host-side mirrors of
+
+    FluxTransformerBlock        fastdm/model/flux.py:78-178
+    FluxSingleTransformerBlock  fastdm/model/flux.py:17-76
+    WanTransformerBlock         fastdm/model/wan.py:19-114   (+ WanAttention, layer/transformer.py:393-535)
+
+Same inputs, outputs and weights (diffusers state-dict names) as the reference classes. The op
+sequence of each block is the reference's, regrouped so that every activation makes one trip
+through HBM per GEMM:
+
+    AdaLN LayerNorm + modulate + per-token quant   -> ops.layernorm_modulate_quant   (1 kernel)
+    qkv projection                                  -> W8A8 GEMM writing the joint [txt|img] buffer
+    slice/.contiguous()/rms_norm x2/cat x3/rope     -> ops.qk_norm_rope_ in place     (1 kernel)
+    attention                                       -> reads q/k/v as strided views, no copies
+    out-proj / ff2 + gate * out + residual          -> GEMM epilogue
+    ff1 / proj_mlp + GELU                           -> GEMM epilogue
+    cat([attn, mlp])  (single block)                -> both producers write one buffer
+"""
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .layers import FeedForward, QLinear, Quantized, load_linear, quantize
+
+
+def _mod(scale: torch.Tensor, shift: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(1 + scale) evaluated in the tensor dtype as the reference does (normalization.py:196), then
+    widened to fp32 for the fused kernel (exact)."""
+    return (1 + scale).float().contiguous(), shift.float().contiguous()
+
+
+class FluxTransformerBlock:
+    def __init__(self, sd, prefix, num_attention_heads, attention_head_dim, quant_type=torch.float8_e4m3fn,
+                 device="cuda", eps=1e-6):
+        p, q, dv = prefix, quant_type, device
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.dim = self.heads * self.hd
+        self.quant_type = q
+        self.eps = eps
+        self.norm1_linear = load_linear(sd, [f"{p}.norm1.linear"], None, dv)              # unquantized: flux.py:288
+        self.norm1_context_linear = load_linear(sd, [f"{p}.norm1_context.linear"], None, dv)
+        self.qkv = load_linear(sd, [f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], q, dv)
+        self.add_qkv_proj = load_linear(sd, [f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], q, dv)
+        self.to_out = load_linear(sd, [f"{p}.attn.to_out.0"], q, dv)
+        self.to_add_out = load_linear(sd, [f"{p}.attn.to_add_out"], q, dv)
+        self.norm_q_weight = sd[f"{p}.attn.norm_q.weight"].to(dv).contiguous()
+        self.norm_k_weight = sd[f"{p}.attn.norm_k.weight"].to(dv).contiguous()
+        self.norm_added_q_weight = sd[f"{p}.attn.norm_added_q.weight"].to(dv).contiguous()
+        self.norm_added_k_weight = sd[f"{p}.attn.norm_added_k.weight"].to(dv).contiguous()
+        self.ff = FeedForward(load_linear(sd, [f"{p}.ff.net.0.proj"], q, dv), load_linear(sd, [f"{p}.ff.net.2"], q, dv))
+        self.ff_context = FeedForward(load_linear(sd, [f"{p}.ff_context.net.0.proj"], q, dv),
+                                      load_linear(sd, [f"{p}.ff_context.net.2"], q, dv))
+        self.scale = self.hd ** -0.5
+
+    def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None):
+        B, S_img, d = hidden_states.shape
+        S_txt = encoder_hidden_states.shape[1]
+        S = S_txt + S_img
+        H, hd, qt = self.heads, self.hd, self.quant_type
+        # AdaLN parameters (M = batch GEMMs, unquantized as in the reference)
+        emb = self.norm1_linear.forward(F.silu(temb))
+        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
+        cemb = self.norm1_context_linear.forward(F.silu(temb))
+        c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = cemb.chunk(6, dim=1)
+
+        hid2 = hidden_states.reshape(B * S_img, d)
+        enc2 = encoder_hidden_states.reshape(B * S_txt, d)
+        # norm1 + modulate + quant (normalization.py:191-199) for both streams
+        a, c = _mod(scale_msa, shift_msa)
+        xq = ops.layernorm_modulate_quant(hid2, a, c, S_img, qt, self.eps)
+        a, c = _mod(c_scale_msa, c_shift_msa)
+        cq = ops.layernorm_modulate_quant(enc2, a, c, S_txt, qt, self.eps)
+        xq, cq = Quantized(*xq[:3]), Quantized(*cq[:3])
+
+        # joint [txt | img] qkv buffer: both projections write their rows, no torch.cat (transformer.py:293-295)
+        qkv = torch.empty((B, S, 3 * d), device=hid2.device, dtype=hidden_states.dtype)
+        for b in range(B):
+            self.add_qkv_proj.forward(cq.rows(b * S_txt, (b + 1) * S_txt), out=qkv[b, :S_txt])
+            self.qkv.forward(xq.rows(b * S_img, (b + 1) * S_img), out=qkv[b, S_txt:])
+            ops.qk_norm_rope_(qkv[b, :S_txt], self.norm_added_q_weight, self.norm_added_k_weight, image_rotary_emb,
+                              H, H, hd, 0, d, 0, self.eps)
+            ops.qk_norm_rope_(qkv[b, S_txt:], self.norm_q_weight, self.norm_k_weight, image_rotary_emb,
+                              H, H, hd, 0, d, S_txt, self.eps)
+        attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale)
+
+        new_hidden = torch.empty_like(hidden_states)
+        new_encoder = torch.empty_like(encoder_hidden_states)
+        g_msa, g_mlp = gate_msa.float().contiguous(), gate_mlp.float().contiguous()
+        cg_msa, cg_mlp = c_gate_msa.float().contiguous(), c_gate_mlp.float().contiguous()
+        for b in range(B):
+            # hidden = hidden + gate_msa * to_out(attn)      (flux.py:153-154)
+            aq = quantize(attn[b, S_txt:], qt)
+            self.to_out.forward(aq, gate=g_msa[b:b + 1], residual=hidden_states[b], rows_per_batch=S_img,
+                                out=new_hidden[b])
+            eq = quantize(attn[b, :S_txt], qt)
+            self.to_add_out.forward(eq, gate=cg_msa[b:b + 1], residual=encoder_hidden_states[b],
+                                    rows_per_batch=S_txt, out=new_encoder[b])
+        # norm2 + modulate + quant, ff with GELU(tanh) epilogue, gate + residual epilogue (flux.py:156-163)
+        a, c = _mod(scale_mlp, shift_mlp)
+        nq = Quantized(*ops.layernorm_modulate_quant(new_hidden.view(B * S_img, d), a, c, S_img, qt, self.eps)[:3])
+        self.ff.forward(nq, gate=g_mlp, residual=new_hidden.view(B * S_img, d), rows_per_batch=S_img,
+                        out=new_hidden.view(B * S_img, d))
+        a, c = _mod(c_scale_mlp, c_shift_mlp)
+        nq = Quantized(*ops.layernorm_modulate_quant(new_encoder.view(B * S_txt, d), a, c, S_txt, qt, self.eps)[:3])
+        self.ff_context.forward(nq, gate=cg_mlp, residual=new_encoder.view(B * S_txt, d), rows_per_batch=S_txt,
+                                out=new_encoder.view(B * S_txt, d))
+        return new_encoder, new_hidden
+
+
+class FluxSingleTransformerBlock:
+    def __init__(self, sd, prefix, num_attention_heads, attention_head_dim, quant_type=torch.float8_e4m3fn,
+                 device="cuda", mlp_ratio=4.0, eps=1e-6):
+        p, q, dv = prefix, quant_type, device
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.dim = self.heads * self.hd
+        self.mlp_hidden_dim = int(self.dim * mlp_ratio)
+        self.quant_type = q
+        self.eps = eps
+        self.norm_linear = load_linear(sd, [f"{p}.norm.linear"], None, dv)
+        self.proj_mlp = load_linear(sd, [f"{p}.proj_mlp"], q, dv)
+        self.proj_out = load_linear(sd, [f"{p}.proj_out"], q, dv)
+        self.qkv = load_linear(sd, [f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], q, dv)
+        self.norm_q_weight = sd[f"{p}.attn.norm_q.weight"].to(dv).contiguous()
+        self.norm_k_weight = sd[f"{p}.attn.norm_k.weight"].to(dv).contiguous()
+        self.scale = self.hd ** -0.5
+
+    def forward(self, hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None):
+        B, S, d = hidden_states.shape
+        H, hd, qt = self.heads, self.hd, self.quant_type
+        emb = self.norm_linear.forward(F.silu(temb))
+        shift_msa, scale_msa, gate = emb.chunk(3, dim=1)
+        hid2 = hidden_states.reshape(B * S, d)
+        a, c = _mod(scale_msa, shift_msa)
+        # one quantised copy of norm_hidden_states feeds both proj_mlp and qkv (flux.py:60-67)
+        xq = Quantized(*ops.layernorm_modulate_quant(hid2, a, c, S, qt, self.eps)[:3])
+        # cat([attn_output, mlp_hidden_states], dim=2) without the cat (flux.py:69)
+        cat = torch.empty((B, S, d + self.mlp_hidden_dim), device=hid2.device, dtype=hidden_states.dtype)
+        cat2 = cat.view(B * S, d + self.mlp_hidden_dim)
+        self.proj_mlp.forward(xq, act="gelu_erf", out=cat2[:, d:])            # F.gelu (erf): flux.py:61
+        qkv = self.qkv.forward(xq).view(B, S, 3 * d)
+        for b in range(B):
+            ops.qk_norm_rope_(qkv[b], self.norm_q_weight, self.norm_k_weight, image_rotary_emb, H, H, hd, 0, d, 0,
+                              self.eps)
+        ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale, out=cat[:, :, :d])
+        cq = quantize(cat2, qt)
+        out = torch.empty_like(hidden_states)
+        # hidden = residual + gate * proj_out(cat)      (flux.py:70-72)
+        self.proj_out.forward(cq, gate=gate.float().contiguous(), residual=hid2, rows_per_batch=S,
+                              out=out.view(B * S, d))
+        return out
+
+
+class WanTransformerBlock:
+    """wan2.1 / wan2.2-A14B text-to-video block (temb [B, 6, dim]; no added_kv_proj)."""
+
+    def __init__(self, sd, prefix, num_heads, head_dim, quant_type=torch.float8_e4m3fn, device="cuda",
+                 cross_attn_norm=True, eps=1e-6):
+        p, q, dv = prefix, quant_type, device
+        self.heads, self.hd = num_heads, head_dim
+        self.dim = num_heads * head_dim
+        self.quant_type = q
+        self.eps = eps
+        self.qkv = load_linear(sd, [f"{p}.attn1.to_q", f"{p}.attn1.to_k", f"{p}.attn1.to_v"], q, dv)
+        self.to_out1 = load_linear(sd, [f"{p}.attn1.to_out.0"], q, dv)
+        self.norm_q1 = sd[f"{p}.attn1.norm_q.weight"].to(dv).contiguous()
+        self.norm_k1 = sd[f"{p}.attn1.norm_k.weight"].to(dv).contiguous()
+        self.to_q2 = load_linear(sd, [f"{p}.attn2.to_q"], q, dv)
+        self.to_kv2 = load_linear(sd, [f"{p}.attn2.to_k", f"{p}.attn2.to_v"], q, dv)
+        self.to_out2 = load_linear(sd, [f"{p}.attn2.to_out.0"], q, dv)
+        self.norm_q2 = sd[f"{p}.attn2.norm_q.weight"].to(dv).contiguous()
+        self.norm_k2 = sd[f"{p}.attn2.norm_k.weight"].to(dv).contiguous()
+        self.cross_attn_norm = cross_attn_norm
+        if cross_attn_norm:
+            self.norm2_weight = sd[f"{p}.norm2.weight"].to(dv).to(torch.float32).reshape(1, -1).contiguous()
+            self.norm2_bias = sd[f"{p}.norm2.bias"].to(dv).to(torch.float32).reshape(1, -1).contiguous()
+        self.ffn = FeedForward(load_linear(sd, [f"{p}.ffn.net.0.proj"], q, dv), load_linear(sd, [f"{p}.ffn.net.2"], q, dv))
+        self.scale_shift_table = sd[f"{p}.scale_shift_table"].to(dv)
+        self.scale = self.hd ** -0.5
+
+    @staticmethod
+    def merge_rotary(rotary_emb, dtype):
+        """cos/sin [1, N, 1, hd] pair -> the [N, hd] cos||sin table (layer/transformer.py:497-498)."""
+        cos, sin = rotary_emb
+        return torch.cat((cos.squeeze()[:, 0::2], sin.squeeze()[:, 1::2]), dim=-1).to(dtype).contiguous()
+
+    def self_attention_qkv(self, xq, B, S, rope_table, pos0=0):
+        """qkv projection + across-heads q/k RMSNorm + RoPE, in place (transformer.py:486-499)."""
+        d, H, hd = self.dim, self.heads, self.hd
+        qkv = self.qkv.forward(xq).view(B, S, 3 * d)
+        for b in range(B):
+            ops.qk_norm_rope_(qkv[b], self.norm_q1, self.norm_k1, rope_table, H, H, hd, 0, d, pos0, self.eps,
+                              across_heads=True)
+        return qkv
+
+    def forward(self, hidden_states, encoder_hidden_states, temb, rotary_emb, sparse_mask=None,
+                block_q=128, block_k=64, attention_fn=None):
+        """attention_fn(qkv [B,S,3d]) -> [B,S,d] lets the Ulysses wrapper replace the local attention."""
+        B, S, d = hidden_states.shape
+        H, hd, qt = self.heads, self.hd, self.quant_type
+        shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = (
+            self.scale_shift_table + temb.float()).chunk(6, dim=1)                      # wan.py:88-91 (fp32)
+        r2 = lambda t: t.reshape(B, d).contiguous()  # noqa: E731
+        hid2 = hidden_states.reshape(B * S, d)
+        rope_table = rotary_emb if torch.is_tensor(rotary_emb) else self.merge_rotary(rotary_emb, hidden_states.dtype)
+
+        # 1. self-attention: (norm1(x) * (1 + scale) + shift) in fp32, one rounding (wan.py:95)
+        xq = Quantized(*ops.layernorm_modulate_quant(hid2, r2(1 + scale_msa), r2(shift_msa), S, qt, self.eps,
+                                                     round_steps=False)[:3])
+        qkv = self.self_attention_qkv(xq, B, S, rope_table)
+        if attention_fn is not None:
+            attn = attention_fn(qkv)
+        else:
+            attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale,
+                                 sparse_mask, block_q, block_k)
+        h1 = torch.empty_like(hid2)
+        # hidden = (hidden.float() + attn_out * gate).type_as(hidden)      (wan.py:97)
+        self.to_out1.forward(quantize(attn.view(B * S, d), qt), gate=r2(gate_msa), residual=hid2, rows_per_batch=S,
+                             round_steps=False, out=h1)
+
+        # 2. cross-attention (wan.py:100-105); K/V come from the (replicated) text tokens
+        if self.cross_attn_norm:
+            nq = Quantized(*ops.layernorm_modulate_quant(h1, self.norm2_weight, self.norm2_bias, B * S, qt, self.eps,
+                                                         round_steps=False)[:3])
+        else:
+            nq = quantize(h1, qt)
+        q2 = self.to_q2.forward(nq)
+        ops.qk_norm_rope_(q2, self.norm_q2, None, None, H, 0, hd, 0, 0, 0, self.eps, across_heads=True)
+        T = encoder_hidden_states.shape[1]
+        kv = self.to_kv2.forward(encoder_hidden_states.reshape(B * T, -1))
+        ops.qk_norm_rope_(kv, self.norm_k2, None, None, H, 0, hd, 0, 0, 0, self.eps, across_heads=True)
+        kv = kv.view(B, T, 2 * d)
+        attn2 = ops.attention(q2.view(B, S, d), kv[:, :, :d], kv[:, :, d:], H, hd, self.scale)
+        h2 = torch.empty_like(hid2)
+        self.to_out2.forward(quantize(attn2.view(B * S, d), qt), residual=h1, rows_per_batch=S, out=h2)  # wan.py:105
+
+        # 3. feed-forward (wan.py:108-112)
+        nq = Quantized(*ops.layernorm_modulate_quant(h2, r2(1 + c_scale_msa), r2(c_shift_msa), S, qt, self.eps,
+                                                     round_steps=False)[:3])
+        out = torch.empty_like(hid2)
+        self.ffn.forward(nq, gate=r2(c_gate_msa), residual=h2, rows_per_batch=S, round_steps=False, out=out)
+        return out.view(B, S, d)

@@ -54,6 +54,7 @@ struct AttnSmem {
 
 struct AttnParams {
   void* o;
+  int64_t o_bs, o_ts;
   const int8_t* mask;
   int B, H, Sq, Sk;
   int n_kv_tiles;
@@ -366,7 +367,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     // ---- epilogue: O / l -> global ----
     const bool row_ok = row < p.Sq;
-    uint16_t* out_row = reinterpret_cast<uint16_t*>(p.o) + (((int64_t)b * p.Sq + row) * p.H + h) * HD;
+    uint16_t* out_row = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ts + (int64_t)h * HD;
     if (t > 0) {
       mbar_wait(o_done(x), (t - 1) & 1u);
       tc_fence_after();
@@ -439,8 +440,8 @@ using namespace fdm;
 extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o,
                             const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
                             int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
-                            int64_t v_ts, int mask_bq, int mask_bk, float scale, int qkv_dtype,
-                            void* stream) {
+                            int64_t v_ts, int64_t o_bs, int64_t o_ts, int mask_bq, int mask_bk,
+                            float scale, int qkv_dtype, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   FDM_REQUIRE(B >= 0 && Sq >= 0 && Sk >= 0 && H > 0, "attn: bad shape");
@@ -456,15 +457,18 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   FDM_REQUIRE(Sk > 0, "attn: empty key sequence");
   FDM_REQUIRE(Sq < (1LL << 31) && Sk <= (int64_t)kMaxKvTiles * kKvTile && H < 65536 && B < 65536,
               "attn: sequence too long (Sk <= %d)", kMaxKvTiles * kKvTile);
-  for (int64_t s : {q_ts, k_ts, v_ts, q_bs, k_bs, v_bs})
+  for (int64_t s : {q_ts, k_ts, v_ts, q_bs, k_bs, v_bs, o_ts, o_bs})
     FDM_REQUIRE(s % 8 == 0, "attn: strides must be multiples of 8 elements (16 bytes)");
   FDM_REQUIRE((uintptr_t)q % 16 == 0 && (uintptr_t)k % 16 == 0 && (uintptr_t)v % 16 == 0 &&
                   (uintptr_t)o % 16 == 0,
               "attn: pointers must be 16-byte aligned");
   FDM_REQUIRE(q_ts >= (int64_t)H * hd && k_ts >= (int64_t)H * hd && v_ts >= (int64_t)H * hd,
               "attn: token stride smaller than H*hd");
+  FDM_REQUIRE(o_ts >= (int64_t)H * hd, "attn: output token stride smaller than H*hd");
   AttnParams p;
   p.o = o;
+  p.o_bs = o_bs;
+  p.o_ts = o_ts;
   p.mask = block_mask;
   p.B = (int)B;
   p.H = H;

@@ -592,6 +592,263 @@ __global__ void __launch_bounds__(256) gelu_mul_generic_kernel(const T* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fused q/k RMSNorm + RoPE, in place on a fused qkv buffer (Attention.forward:
+// fastdm/layer/transformer.py:275-298; WanAttention.forward: :490-499).
+// ------------------------------------------------------------------------------------------------
+// interleaved rotation of the 8 elements starting at column `col` (within the head) of cache row `cs`
+template <typename T>
+__device__ __forceinline__ void rope8(float (&x)[8], const T* __restrict__ cs, int col, int half) {
+  const uint2 craw = *reinterpret_cast<const uint2*>(cs + (col >> 1));
+  const uint2 sraw = *reinterpret_cast<const uint2*>(cs + half + (col >> 1));
+  float c[4], sn[4];
+  if (Elem<T>::kId == FDM_BF16) {
+    c[0] = bf16lo(craw.x); c[1] = bf16hi(craw.x); c[2] = bf16lo(craw.y); c[3] = bf16hi(craw.y);
+    sn[0] = bf16lo(sraw.x); sn[1] = bf16hi(sraw.x); sn[2] = bf16lo(sraw.y); sn[3] = bf16hi(sraw.y);
+  } else {
+    c[0] = f16lo(craw.x); c[1] = f16hi(craw.x); c[2] = f16lo(craw.y); c[3] = f16hi(craw.y);
+    sn[0] = f16lo(sraw.x); sn[1] = f16hi(sraw.x); sn[2] = f16lo(sraw.y); sn[3] = f16hi(sraw.y);
+  }
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const float x1 = x[2 * p], x2 = x[2 * p + 1];
+    x[2 * p] = __fsub_rn(round_to<T>(__fmul_rn(x1, c[p])), round_to<T>(__fmul_rn(x2, sn[p])));
+    x[2 * p + 1] = __fadd_rn(round_to<T>(__fmul_rn(x2, c[p])), round_to<T>(__fmul_rn(x1, sn[p])));
+  }
+}
+
+// per-head norm: LANES = head_size/8 lanes per (token, head) row
+template <typename T, int LANES>
+__global__ void __launch_bounds__(256) qk_norm_rope_head_kernel(
+    T* __restrict__ buf, const T* __restrict__ wq, const T* __restrict__ wk, const T* __restrict__ cs,
+    int64_t tokens, int q_heads, int k_heads, int head_size, int64_t token_stride, int64_t q_offset,
+    int64_t k_offset, int64_t pos0, int64_t cs_stride, float eps) {
+  constexpr int RPW = 32 / LANES;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LANES, li = lane % LANES;
+  const int heads = q_heads + k_heads;
+  const int64_t rows = tokens * heads;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t warp_count = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float wqv[8], wkv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) wqv[j] = wkv[j] = 1.f;
+  if (wq) unpack8<T>(ldg128(wq + li * 8), wqv);
+  if (wk) unpack8<T>(ldg128(wk + li * 8), wkv);
+  const float inv_cols = 1.0f / (float)head_size;
+  const int half = head_size >> 1;
+  constexpr int UNROLL = 4;
+  for (int64_t base = warp_global * RPW; base < rows; base += warp_count * RPW * UNROLL) {
+    U128 raw[UNROLL];
+    T* ptr[UNROLL];
+    int64_t tok[UNROLL];
+    bool isk[UNROLL], ok[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t r = base + (int64_t)u * warp_count * RPW + sub;
+      ok[u] = r < rows;
+      tok[u] = r / heads;
+      const int hh = (int)(r - tok[u] * heads);
+      isk[u] = hh >= q_heads;
+      ptr[u] = buf + tok[u] * token_stride +
+               (isk[u] ? k_offset + (int64_t)(hh - q_heads) * head_size : q_offset + (int64_t)hh * head_size) +
+               li * 8;
+      raw[u] = ok[u] ? ldg128(ptr[u]) : U128{0, 0, 0, 0};
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float f[8];
+      unpack8<T>(raw[u], f);
+      const bool do_norm = isk[u] ? (wk != nullptr) : (wq != nullptr);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+      ss = warp_sum<LANES>(ss);
+      if (do_norm) {
+        const float rs = rsqrtf(ss * inv_cols + eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = round_to<T>(round_to<T>(f[j] * rs) * (isk[u] ? wkv[j] : wqv[j]));
+      }
+      if (ok[u]) {
+        if (cs != nullptr) rope8<T>(f, cs + (pos0 + tok[u]) * cs_stride, li * 8, half);
+        stg128(ptr[u], pack8<T>(f));
+      }
+    }
+  }
+}
+
+// across-heads norm (Wan): one CTA per (token, q|k); the heads*head_size row lives in registers
+template <typename T, int VPT>
+__global__ void __launch_bounds__(512) qk_norm_rope_row_kernel(
+    T* __restrict__ buf, const T* __restrict__ wq, const T* __restrict__ wk, const T* __restrict__ cs,
+    int q_heads, int k_heads, int head_size, int64_t token_stride, int64_t q_offset, int64_t k_offset,
+    int64_t pos0, int64_t cs_stride, float eps) {
+  __shared__ float red[32];
+  const int64_t tok = blockIdx.x >> 1;
+  const bool isk = blockIdx.x & 1;
+  const int heads = isk ? k_heads : q_heads;
+  if (heads == 0) return;
+  const int cols = heads * head_size;
+  const int nvec = cols >> 3;
+  T* row = buf + tok * token_stride + (isk ? k_offset : q_offset);
+  const T* w = isk ? wk : wq;
+  U128 raw[VPT];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      raw[i] = ldg128(row + (int64_t)v * 8);
+      float f[8];
+      unpack8<T>(raw[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
+    }
+  }
+  ss = block_sum(ss, red);
+  const float rs = rsqrtf(ss / (float)cols + eps);
+  const int half = head_size >> 1;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float f[8];
+      unpack8<T>(raw[i], f);
+      if (w != nullptr) {
+        float wv[8];
+        unpack8<T>(ldg128(w + (int64_t)v * 8), wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = round_to<T>(round_to<T>(f[j] * rs) * wv[j]);
+      }
+      if (cs != nullptr) rope8<T>(f, cs + (pos0 + tok) * cs_stride, (v * 8) % head_size, half);
+      stg128(row + (int64_t)v * 8, pack8<T>(f));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (no affine) * A + C, then per-token quantisation -- the AdaLN "modulate" in front of
+// every quantised linear, fused with that linear's quant prologue:
+//   FLUX / SD3 / Qwen (ROUND_STEPS): y = T( T( T(LN(x)) * A ) + C ),  A = T(1 + scale), C = shift
+//       fastdm/layer/normalization.py:191-199,228-234; fastdm/model/flux.py:156-158,170-171
+//   Wan (fp32 chain):                y = T( LN(x) * A + C ),          A = 1 + scale (fp32), C = shift
+//       fastdm/model/wan.py:95,108 ; norm2 (:101): A = weight, C = bias
+// A and C are fp32 [batches, cols]; row r uses batch r / rows_per_batch. Output: quantised y
+// (MODE as above) and/or y itself (y_out may be NULL).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int MODE /*0 fp8, 2 int8 asym, 3 none*/, bool ROUND_STEPS, int VPT>
+__global__ void __launch_bounds__(512) ln_mod_quant_kernel(
+    const T* __restrict__ in, const float* __restrict__ A, const float* __restrict__ C,
+    uint8_t* __restrict__ out, float* __restrict__ scale, int32_t* __restrict__ azp,
+    T* __restrict__ y_out, int cols, int64_t in_row_stride, int64_t y_row_stride,
+    int64_t rows_per_batch, float eps) {
+  __shared__ float red[64];
+  const int64_t row = blockIdx.x;
+  const int nvec = cols >> 3;
+  const T* src = in + row * in_row_stride;
+  const int64_t bidx = row / rows_per_batch;
+  const float* Ar = A ? A + bidx * cols : nullptr;
+  const float* Cr = C ? C + bidx * cols : nullptr;
+  U128 raw[VPT];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      raw[i] = ldg128_stream(src + (int64_t)v * 8);
+      float f[8];
+      unpack8<T>(raw[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[j];
+    }
+  }
+  const float mean = block_sum(sum, red) / (float)cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float f[8];
+      unpack8<T>(raw[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = f[j] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
+  float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float f[8];
+      unpack8<T>(raw[i], f);
+      float a[8], c[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] = 1.f;
+        c[j] = 0.f;
+      }
+      if (Ar) {
+        const float4 a0 = *reinterpret_cast<const float4*>(Ar + v * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(Ar + v * 8 + 4);
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      }
+      if (Cr) {
+        const float4 c0 = *reinterpret_cast<const float4*>(Cr + v * 8);
+        const float4 c1 = *reinterpret_cast<const float4*>(Cr + v * 8 + 4);
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float n = (f[j] - mean) * rstd;
+        if (ROUND_STEPS) {
+          n = round_to<T>(n);
+          if (Ar) n = round_to<T>(__fmul_rn(n, a[j]));
+          if (Cr) n = __fadd_rn(n, c[j]);
+        } else {
+          if (Ar) n = __fmul_rn(n, a[j]);
+          if (Cr) n = __fadd_rn(n, c[j]);
+        }
+        f[j] = round_to<T>(n);
+        mn = fminf(mn, f[j]);
+        mx = fmaxf(mx, f[j]);
+      }
+      raw[i] = pack8<T>(f);
+      if (y_out) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
+    }
+  }
+  if (MODE == 3) return;
+  MinMax r = block_minmax(mn, mx, red);
+  const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(r.mn, r.mx, fp8_amax_floor<T>());
+  if (threadIdx.x == 0) {
+    scale[row] = p.scale;
+    if (MODE == 2) azp[row] = p.zp;
+  }
+  uint8_t* dst = out + row * (int64_t)cols;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float f[8], q[8];
+      unpack8<T>(raw[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) q[j] = qtransform<MODE == 3 ? 0 : MODE>(f[j], p);
+      uint32_t lo, hi;
+      if (MODE == 0) {
+        lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
+        hi = cvt_e4m3x4(q[4], q[5], q[6], q[7]);
+      } else {
+        lo = pack_s8x4(q[0], q[1], q[2], q[3]);
+        hi = pack_s8x4(q[4], q[5], q[6], q[7]);
+      }
+      stg64(dst + (int64_t)v * 8, lo, hi);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Ulysses layout helpers: [S, H, hd] <-> [P, S, H/P, hd], 16-byte vectors
 // ------------------------------------------------------------------------------------------------
 template <bool PACK>
@@ -751,6 +1008,151 @@ int fdm_gelu_and_mul(const void* in, void* out, int64_t rows, int64_t d, int64_t
     return FDM_ERR_UNSUPPORTED;
   }
   FDM_LAUNCH_CHECK("gelu_and_mul kernel launch");
+  return FDM_OK;
+}
+
+int fdm_qk_norm_rope(void* buf, const void* wq, const void* wk, const void* cos_sin, int64_t tokens,
+                     int q_heads, int k_heads, int head_size, int64_t token_stride, int64_t q_offset,
+                     int64_t k_offset, int64_t pos0, int64_t cs_row_stride, float eps,
+                     int across_heads, int dtype, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(tokens >= 0 && q_heads >= 0 && k_heads >= 0 && head_size > 0, "qk_norm_rope: bad shape");
+  if (tokens == 0 || q_heads + k_heads == 0) return FDM_OK;
+  FDM_REQUIRE(buf != nullptr, "qk_norm_rope: null buffer");
+  FDM_REQUIRE(head_size % 8 == 0 && token_stride % 8 == 0 && q_offset % 8 == 0 && k_offset % 8 == 0 &&
+                  (uintptr_t)buf % 16 == 0,
+              "qk_norm_rope: head_size / strides / offsets must keep 16-byte alignment");
+  FDM_REQUIRE((wq == nullptr || (uintptr_t)wq % 16 == 0) && (wk == nullptr || (uintptr_t)wk % 16 == 0),
+              "qk_norm_rope: weights must be 16-byte aligned");
+  if (cos_sin)
+    FDM_REQUIRE(cs_row_stride % 4 == 0 && (uintptr_t)cos_sin % 8 == 0 && pos0 >= 0,
+                "qk_norm_rope: cos/sin cache rows must be 8-byte aligned");
+  FDM_REQUIRE(dtype == FDM_BF16 || dtype == FDM_F16, "qk_norm_rope: dtype must be bf16 or f16");
+  cudaStream_t st = (cudaStream_t)stream;
+#define QKNR_HEAD(T, L)                                                                              \
+  qk_norm_rope_head_kernel<T, L><<<g, 256, 0, st>>>((T*)buf, (const T*)wq, (const T*)wk,              \
+                                                    (const T*)cos_sin, tokens, q_heads, k_heads,      \
+                                                    head_size, token_stride, q_offset, k_offset, pos0, \
+                                                    cs_row_stride, eps)
+#define QKNR_ROW(T, V)                                                                               \
+  qk_norm_rope_row_kernel<T, V><<<(unsigned)(tokens * 2), block, 0, st>>>(                           \
+      (T*)buf, (const T*)wq, (const T*)wk, (const T*)cos_sin, q_heads, k_heads, head_size,            \
+      token_stride, q_offset, k_offset, pos0, cs_row_stride, eps)
+  if (!across_heads) {
+    FDM_REQUIRE(head_size == 64 || head_size == 128 || head_size == 256 || head_size == 32,
+                "qk_norm_rope: per-head mode supports head_size 32/64/128/256");
+    const int lanes = head_size / 8;
+    const int rpw = 32 / lanes;
+    const int64_t rows = tokens * (q_heads + k_heads);
+    int64_t want = ((rows + rpw - 1) / rpw + 8 * 4 - 1) / (8 * 4);
+    const int64_t cap = (int64_t)num_sms() * 32;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    const unsigned g = (unsigned)want;
+    if (dtype == FDM_BF16) {
+      if (lanes == 4) QKNR_HEAD(__nv_bfloat16, 4);
+      else if (lanes == 8) QKNR_HEAD(__nv_bfloat16, 8);
+      else if (lanes == 16) QKNR_HEAD(__nv_bfloat16, 16);
+      else QKNR_HEAD(__nv_bfloat16, 32);
+    } else {
+      if (lanes == 4) QKNR_HEAD(__half, 4);
+      else if (lanes == 8) QKNR_HEAD(__half, 8);
+      else if (lanes == 16) QKNR_HEAD(__half, 16);
+      else QKNR_HEAD(__half, 32);
+    }
+  } else {
+    FDM_REQUIRE(tokens * 2 < (1LL << 31), "qk_norm_rope: too many tokens");
+    const int cols = (q_heads > k_heads ? q_heads : k_heads) * head_size;
+    const int nvec = cols / 8;
+    FDM_REQUIRE(nvec <= 512 * 8, "qk_norm_rope: row too long");
+    int block = (((nvec + 3) / 4 + 31) / 32) * 32;
+    if (block > 512) block = 512;
+    const int vpt = (nvec + block - 1) / block;
+    if (dtype == FDM_BF16) {
+      if (vpt <= 1) QKNR_ROW(__nv_bfloat16, 1);
+      else if (vpt <= 2) QKNR_ROW(__nv_bfloat16, 2);
+      else if (vpt <= 4) QKNR_ROW(__nv_bfloat16, 4);
+      else QKNR_ROW(__nv_bfloat16, 8);
+    } else {
+      if (vpt <= 1) QKNR_ROW(__half, 1);
+      else if (vpt <= 2) QKNR_ROW(__half, 2);
+      else if (vpt <= 4) QKNR_ROW(__half, 4);
+      else QKNR_ROW(__half, 8);
+    }
+  }
+#undef QKNR_HEAD
+#undef QKNR_ROW
+  FDM_LAUNCH_CHECK("qk_norm_rope kernel launch");
+  return FDM_OK;
+}
+
+}  // extern "C"
+
+template <typename T, int MODE, bool RS>
+static void launch_lnq(const void* in, const float* A, const float* C, void* out, float* scale,
+                       int32_t* azp, void* y, int64_t rows, int cols, int64_t is, int64_t ys,
+                       int64_t rpb, float eps, cudaStream_t st) {
+  const int nvec = cols / 8;
+  int block = (((nvec + 3) / 4 + 31) / 32) * 32;
+  if (block > 512) block = 512;
+  const int vpt = (nvec + block - 1) / block;
+  const unsigned g = (unsigned)rows;
+#define LNQ(V)                                                                                      \
+  ln_mod_quant_kernel<T, MODE, RS, V><<<g, block, 0, st>>>((const T*)in, A, C, (uint8_t*)out, scale, \
+                                                           azp, (T*)y, cols, is, ys, rpb, eps)
+  if (vpt <= 1) LNQ(1);
+  else if (vpt <= 2) LNQ(2);
+  else if (vpt <= 4) LNQ(4);
+  else LNQ(8);
+#undef LNQ
+}
+
+extern "C" {
+
+int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* add, void* out,
+                                 float* scale, int32_t* azp, void* y_out, int64_t rows, int64_t cols,
+                                 int64_t in_row_stride, int64_t y_row_stride, int64_t rows_per_batch,
+                                 float eps, int round_steps, int in_dtype, int out_dtype,
+                                 void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(rows >= 0 && cols > 0 && rows_per_batch > 0, "layernorm_modulate_quant: bad shape");
+  if (rows == 0) return FDM_OK;
+  FDM_REQUIRE(in != nullptr, "layernorm_modulate_quant: null input");
+  FDM_REQUIRE(in_dtype == FDM_BF16, "layernorm_modulate_quant: input must be bf16");
+  FDM_REQUIRE(cols % 8 == 0 && cols <= 512 * 8 * 8 && in_row_stride % 8 == 0 &&
+                  (uintptr_t)in % 16 == 0,
+              "layernorm_modulate_quant: cols must be a multiple of 8 (<= 32768), 16-byte aligned rows");
+  FDM_REQUIRE((mul == nullptr || (uintptr_t)mul % 16 == 0) && (add == nullptr || (uintptr_t)add % 16 == 0),
+              "layernorm_modulate_quant: mul/add must be 16-byte aligned fp32");
+  FDM_REQUIRE(y_out == nullptr || (y_row_stride % 8 == 0 && (uintptr_t)y_out % 16 == 0),
+              "layernorm_modulate_quant: y_out alignment");
+  FDM_REQUIRE(rows < (1LL << 31), "layernorm_modulate_quant: too many rows");
+  const bool q8 = out_dtype == FDM_E4M3, s8 = out_dtype == FDM_S8;
+  if (q8 || s8) {
+    FDM_REQUIRE(out && scale && (!s8 || azp), "layernorm_modulate_quant: null output");
+    FDM_REQUIRE((uintptr_t)out % 8 == 0, "layernorm_modulate_quant: out alignment");
+  } else {
+    FDM_REQUIRE(y_out != nullptr, "layernorm_modulate_quant: nothing to write");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  using B = __nv_bfloat16;
+  const int c = (int)cols;
+#define LNQ_CALL(MODE)                                                                               \
+  do {                                                                                               \
+    if (round_steps)                                                                                 \
+      launch_lnq<B, MODE, true>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride,        \
+                                y_row_stride, rows_per_batch, eps, st);                              \
+    else                                                                                             \
+      launch_lnq<B, MODE, false>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride,       \
+                                 y_row_stride, rows_per_batch, eps, st);                             \
+  } while (0)
+  if (q8) LNQ_CALL(0);
+  else if (s8) LNQ_CALL(2);
+  else LNQ_CALL(3);
+#undef LNQ_CALL
+  FDM_LAUNCH_CHECK("layernorm_modulate_quant kernel launch");
   return FDM_OK;
 }
 

@@ -56,6 +56,12 @@ struct GemmParams {
   int act;
   int tiles_m, tiles_n;
   int vec_store;
+  // fused residual epilogue: d = residual + gate[row / rows_per_batch, n] * T(linear)
+  const float* gate;     // fp32 [batches, N] or NULL
+  const void* residual;  // out_dtype [M, N] (row stride ldr) or NULL; may alias d
+  int64_t ldr;
+  int64_t rows_per_batch;
+  int round_steps;       // 1: T(gate * x) before the residual add (bf16 tensor-op chain)
 };
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
@@ -253,13 +259,52 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         if (row_ok) {
           const int col0 = n0 + c * 32;
+          const bool bf = p.out_dtype == FDM_BF16;
+          if (p.gate != nullptr || p.residual != nullptr) {
+            // reference chains (flux.py:153-154,161-163,69-72; wan.py:97,105,112): the linear's output
+            // is a T tensor, then gate * out (+ rounding for bf16 tensor ops), then residual + .
+            const float* grow = p.gate ? p.gate + (int64_t)(row / p.rows_per_batch) * p.N + col0 : nullptr;
+            const uint16_t* rrow = p.residual
+                                       ? reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)row * p.ldr + col0
+                                       : nullptr;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.N) {
+                float gq[8], rq[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  gq[j] = 1.f;
+                  rq[j] = 0.f;
+                }
+                if (grow) {
+                  const float4 g0 = *reinterpret_cast<const float4*>(grow + q * 8);
+                  const float4 g1 = *reinterpret_cast<const float4*>(grow + q * 8 + 4);
+                  gq[0] = g0.x; gq[1] = g0.y; gq[2] = g0.z; gq[3] = g0.w;
+                  gq[4] = g1.x; gq[5] = g1.y; gq[6] = g1.z; gq[7] = g1.w;
+                }
+                if (rrow) {
+                  const U128 rv = ldg128(rrow + q * 8);
+                  if (bf) unpack8<__nv_bfloat16>(rv, rq); else unpack8<__half>(rv, rq);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float x = bf ? round_to<__nv_bfloat16>(v[q * 8 + j]) : round_to<__half>(v[q * 8 + j]);
+                  if (grow) {
+                    x = __fmul_rn(x, gq[j]);
+                    if (p.round_steps) x = bf ? round_to<__nv_bfloat16>(x) : round_to<__half>(x);
+                  }
+                  v[q * 8 + j] = __fadd_rn(rq[j], x);
+                }
+              }
+            }
+          }
           if (p.vec_store) {
             uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + col0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (col0 + q * 8 < p.N) {
                 U128 o;
-                if (p.out_dtype == FDM_BF16) {
+                if (bf) {
                   o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
                   o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
                   o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
@@ -277,7 +322,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               if (col0 + j < p.N) {
-                if (p.out_dtype == FDM_BF16)
+                if (bf)
                   reinterpret_cast<__nv_bfloat16*>(p.d)[(int64_t)row * p.ldd + col0 + j] =
                       __float2bfloat16_rn(v[j]);
                 else
@@ -326,7 +371,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 static int gemm_common(bool int8, const void* a, const void* b, const float* scale_a,
                        const float* scale_b, const int32_t* azp_adj, const int32_t* azp,
                        const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
-                       int64_t ldb, int64_t ldd, int out_dtype, int act, void* stream) {
+                       int64_t ldb, int64_t ldd, int out_dtype, int act, const float* gate,
+                       const void* residual, int64_t ldr, int64_t rows_per_batch, int round_steps,
+                       void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   FDM_REQUIRE(M >= 0 && N >= 0 && K > 0, "gemm: bad shape M=%lld N=%lld K=%lld", (long long)M,
@@ -388,6 +435,17 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   p.tiles_m = (int)tiles_m;
   p.tiles_n = (int)tiles_n;
   p.vec_store = (ldd % 8 == 0 && (uintptr_t)d % 16 == 0) ? 1 : 0;
+  if (gate != nullptr || residual != nullptr) {
+    FDM_REQUIRE(rows_per_batch > 0, "gemm: rows_per_batch must be positive");
+    FDM_REQUIRE(gate == nullptr || (uintptr_t)gate % 16 == 0, "gemm: gate must be 16-byte aligned fp32");
+    FDM_REQUIRE(residual == nullptr || (ldr >= N && ldr % 8 == 0 && (uintptr_t)residual % 16 == 0),
+                "gemm: residual needs ldr >= N, ldr %% 8 == 0 and 16-byte alignment");
+  }
+  p.gate = gate;
+  p.residual = residual;
+  p.ldr = ldr;
+  p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
+  p.round_steps = round_steps;
   cudaStream_t st = (cudaStream_t)stream;
   if (int8) {
     if (bn == 256) return launch_gemm<true, 256>(ta, tb, p, st);
@@ -407,7 +465,7 @@ int fdm_gemm_fp8(const void* a, const void* b, const float* scale_a, const float
                  const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
                  int64_t ldb, int64_t ldd, int out_dtype, int act, void* stream) {
   return fdm::gemm_common(false, a, b, scale_a, scale_b, nullptr, nullptr, bias, d, M, N, K, lda,
-                          ldb, ldd, out_dtype, act, stream);
+                          ldb, ldd, out_dtype, act, nullptr, nullptr, 0, 1, 0, stream);
 }
 
 int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const float* scale_b,
@@ -415,7 +473,27 @@ int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const floa
                   int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int out_dtype,
                   int act, void* stream) {
   return fdm::gemm_common(true, a, b, scale_a, scale_b, azp_adj, azp, bias, d, M, N, K, lda, ldb,
-                          ldd, out_dtype, act, stream);
+                          ldd, out_dtype, act, nullptr, nullptr, 0, 1, 0, stream);
+}
+
+int fdm_gemm_fp8_residual(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                          const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
+                          int64_t ldb, int64_t ldd, int out_dtype, int act, const float* gate,
+                          const void* residual, int64_t ldr, int64_t rows_per_batch, int round_steps,
+                          void* stream) {
+  return fdm::gemm_common(false, a, b, scale_a, scale_b, nullptr, nullptr, bias, d, M, N, K, lda,
+                          ldb, ldd, out_dtype, act, gate, residual, ldr, rows_per_batch, round_steps,
+                          stream);
+}
+
+int fdm_gemm_int8_residual(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                           const int32_t* azp_adj, const int32_t* azp, const void* bias, void* d,
+                           int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
+                           int out_dtype, int act, const float* gate, const void* residual,
+                           int64_t ldr, int64_t rows_per_batch, int round_steps, void* stream) {
+  return fdm::gemm_common(true, a, b, scale_a, scale_b, azp_adj, azp, bias, d, M, N, K, lda, ldb,
+                          ldd, out_dtype, act, gate, residual, ldr, rows_per_batch, round_steps,
+                          stream);
 }
 
 }  // extern "C"

@@ -213,30 +213,42 @@ def _check_mm(a, b, scale_a, scale_b, out_dtype, bias, what, qdtype):
     return m, n, k
 
 
-@torch.library.custom_op("fastdm_b200::gemm_fp8", mutates_args=())
-def _gemm_fp8(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
-              out_dtype: torch.dtype, bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
-    m, n, k = _check_mm(a, b, scale_a, scale_b, out_dtype, bias, "fp8_matmul", torch.float8_e4m3fn)
-    out = torch.empty((m, n), device=a.device, dtype=out_dtype)
+def _check_fused(out, m, n, out_dtype, gate, residual, rows_per_batch, what):
+    if out.shape != (m, n) or out.dtype != out_dtype or out.stride(1) != 1 or not out.is_cuda:
+        raise RuntimeError(f"fastdm_b200.{what}: out must be a [M, N] {out_dtype} CUDA tensor with unit column stride")
+    if gate is not None:
+        if gate.dtype != torch.float32 or gate.ndim != 2 or gate.shape[1] != n or not gate.is_contiguous():
+            raise RuntimeError(f"fastdm_b200.{what}: gate must be contiguous float32 [batches, N]")
+        if rows_per_batch <= 0 or gate.shape[0] * rows_per_batch < m:
+            raise RuntimeError(f"fastdm_b200.{what}: gate rows * rows_per_batch must cover M")
+    if residual is not None:
+        if residual.shape != (m, n) or residual.dtype != out_dtype or residual.stride(1) != 1:
+            raise RuntimeError(f"fastdm_b200.{what}: residual must be [M, N] of out_dtype with unit column stride")
+
+
+@torch.library.custom_op("fastdm_b200::gemm_fp8_", mutates_args=("out",))
+def _gemm_fp8(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
+              bias: Optional[torch.Tensor], act: int, gate: Optional[torch.Tensor],
+              residual: Optional[torch.Tensor], rows_per_batch: int, round_steps: bool) -> None:
+    m, n, k = _check_mm(a, b, scale_a, scale_b, out.dtype, bias, "fp8_matmul", torch.float8_e4m3fn)
+    _check_fused(out, m, n, out.dtype, gate, residual, rows_per_batch, "fp8_matmul")
     with torch.cuda.device(a.device):
-        rc = _lib.load().fdm_gemm_fp8(a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(),
-                                      _ptr(bias), out.data_ptr(), m, n, k,
-                                      a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k, n,
-                                      _DT[out_dtype], act, _stream(a))
+        rc = _lib.load().fdm_gemm_fp8_residual(
+            a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(), _ptr(bias), out.data_ptr(), m, n, k,
+            a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k, out.stride(0) if m > 1 else n,
+            _DT[out.dtype], act, _ptr(gate), _ptr(residual),
+            (residual.stride(0) if m > 1 else n) if residual is not None else 0, max(rows_per_batch, 1),
+            1 if round_steps else 0, _stream(a))
     _lib.check(rc, "fp8_matmul")
-    return out
 
 
-@_gemm_fp8.register_fake
-def _(a, b, scale_a, scale_b, out_dtype, bias, act):
-    return a.new_empty((a.shape[0], b.shape[1]), dtype=out_dtype)
-
-
-@torch.library.custom_op("fastdm_b200::gemm_int8", mutates_args=())
-def _gemm_int8(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
-               out_dtype: torch.dtype, azp_adj: Optional[torch.Tensor], azp: Optional[torch.Tensor],
-               bias: Optional[torch.Tensor], act: int) -> torch.Tensor:
-    m, n, k = _check_mm(a, b, scale_a, scale_b, out_dtype, bias, "int8_matmul", torch.int8)
+@torch.library.custom_op("fastdm_b200::gemm_int8_", mutates_args=("out",))
+def _gemm_int8(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
+               azp_adj: Optional[torch.Tensor], azp: Optional[torch.Tensor], bias: Optional[torch.Tensor], act: int,
+               gate: Optional[torch.Tensor], residual: Optional[torch.Tensor], rows_per_batch: int,
+               round_steps: bool) -> None:
+    m, n, k = _check_mm(a, b, scale_a, scale_b, out.dtype, bias, "int8_matmul", torch.int8)
+    _check_fused(out, m, n, out.dtype, gate, residual, rows_per_batch, "int8_matmul")
     if (azp is None) != (azp_adj is None):
         raise RuntimeError("fastdm_b200.int8_matmul: azp and azp_adj must be given together")
     if azp is not None:
@@ -246,27 +258,22 @@ def _gemm_int8(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b:
             raise RuntimeError("fastdm_b200.int8_matmul: azp / azp_adj must be int32")
         if not (azp.is_contiguous() and azp_adj.is_contiguous()):
             raise RuntimeError("fastdm_b200.int8_matmul: azp / azp_adj must be contiguous")
-    out = torch.empty((m, n), device=a.device, dtype=out_dtype)
     with torch.cuda.device(a.device):
-        rc = _lib.load().fdm_gemm_int8(a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(),
-                                       _ptr(azp_adj), _ptr(azp), _ptr(bias), out.data_ptr(), m, n, k,
-                                       a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k, n,
-                                       _DT[out_dtype], act, _stream(a))
+        rc = _lib.load().fdm_gemm_int8_residual(
+            a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(), _ptr(azp_adj), _ptr(azp), _ptr(bias),
+            out.data_ptr(), m, n, k, a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k,
+            out.stride(0) if m > 1 else n, _DT[out.dtype], act, _ptr(gate), _ptr(residual),
+            (residual.stride(0) if m > 1 else n) if residual is not None else 0, max(rows_per_batch, 1),
+            1 if round_steps else 0, _stream(a))
     _lib.check(rc, "int8_matmul")
-    return out
-
-
-@_gemm_int8.register_fake
-def _(a, b, scale_a, scale_b, out_dtype, azp_adj, azp, bias, act):
-    return a.new_empty((a.shape[0], b.shape[1]), dtype=out_dtype)
 
 
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-@torch.library.custom_op("fastdm_b200::attn_fwd", mutates_args=())
-def _attn_fwd(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_heads: int, head_dim: int,
-              scale: float, block_mask: Optional[torch.Tensor], mask_bq: int, mask_bk: int) -> torch.Tensor:
+@torch.library.custom_op("fastdm_b200::attn_fwd_", mutates_args=("out",))
+def _attn_fwd(out: torch.Tensor, query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_heads: int,
+              head_dim: int, scale: float, block_mask: Optional[torch.Tensor], mask_bq: int, mask_bk: int) -> None:
     what = "scaled_dot_product_attention"
     _cuda(query, what)
     if query.ndim != 3 or key.ndim != 3 or value.ndim != 3:
@@ -279,6 +286,8 @@ def _attn_fwd(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_h
         raise RuntimeError(f"fastdm_b200.{what}: batch / kv length mismatch")
     if not (query.dtype == key.dtype == value.dtype):
         raise RuntimeError(f"fastdm_b200.{what}: q/k/v dtypes differ")
+    if out.shape != query.shape or out.stride(2) != 1 or out.dtype != _attn_out_dtype(query.dtype):
+        raise RuntimeError(f"fastdm_b200.{what}: out must be [batch, seq, heads*head_dim] with unit last stride")
     ts = []
     for t in (query, key, value):
         # last-dim slices of a fused qkv projection are legal (layer/transformer.py:269,300)
@@ -287,8 +296,6 @@ def _attn_fwd(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_h
             t = t.contiguous()
         ts.append(t)
     q, k, v = ts
-    out_dtype = torch.float16 if query.dtype == torch.float16 else torch.bfloat16
-    out = torch.empty((b, sq, c), device=query.device, dtype=out_dtype)
     if block_mask is not None:
         block_mask = block_mask.to(torch.int8).contiguous()
         nbq, nbk = -(-sq // mask_bq), -(-sk // mask_bk)
@@ -299,14 +306,118 @@ def _attn_fwd(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_h
         rc = _lib.load().fdm_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(block_mask),
                                       b, sq, sk, num_heads, head_dim,
                                       q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
+                                      out.stride(0), out.stride(1),
                                       mask_bq, mask_bk, float(scale), _dt(q, what), _stream(q))
     _lib.check(rc, what)
+
+
+def _attn_out_dtype(dt):
+    return torch.float16 if dt == torch.float16 else torch.bfloat16
+
+
+def attention(query, key, value, num_heads, head_dim, scale=None, block_mask=None, mask_bq=128, mask_bk=64,
+              out=None):
+    """softmax(scale * Q K^T [+ block mask]) V; `out` may be a column slice of a wider buffer."""
+    if scale is None:
+        scale = head_dim ** -0.5
+    if out is None:
+        out = torch.empty(query.shape, device=query.device, dtype=_attn_out_dtype(query.dtype))
+    torch.ops.fastdm_b200.attn_fwd_(out, query, key, value, num_heads, head_dim, scale, block_mask, mask_bq, mask_bk)
     return out
 
 
-@_attn_fwd.register_fake
-def _(query, key, value, num_heads, head_dim, scale, block_mask, mask_bq, mask_bk):
-    return query.new_empty(query.shape, dtype=torch.float16 if query.dtype == torch.float16 else torch.bfloat16)
+# ------------------------------------------------------------------------------------------------
+# fused block ops
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("fastdm_b200::qk_norm_rope_", mutates_args=("buf",))
+def _qk_norm_rope(buf: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor],
+                  cos_sin: Optional[torch.Tensor], q_heads: int, k_heads: int, head_size: int, q_offset: int,
+                  k_offset: int, pos0: int, eps: float, across_heads: bool) -> None:
+    what = "qk_norm_rope"
+    _cuda(buf, what)
+    if buf.ndim != 2 or buf.stride(1) != 1:
+        raise RuntimeError(f"fastdm_b200.{what}: buf must be [tokens, features] with unit column stride")
+    tokens, width = buf.shape
+    if q_offset + q_heads * head_size > width or k_offset + k_heads * head_size > width:
+        raise RuntimeError(f"fastdm_b200.{what}: q/k column ranges exceed the buffer width")
+    wn = head_size * (1 if not across_heads else 1)
+    for w, hn in ((wq, q_heads), (wk, k_heads)):
+        if w is not None:
+            need = head_size * hn if across_heads else head_size
+            if w.numel() != need or w.dtype != buf.dtype or not w.is_contiguous():
+                raise RuntimeError(f"fastdm_b200.{what}: norm weight must be contiguous [{need}] of the buffer dtype")
+    cs = cos_sin
+    if cs is not None:
+        if cs.ndim != 2 or cs.shape[1] != head_size or cs.shape[0] < pos0 + tokens:
+            raise RuntimeError(f"fastdm_b200.{what}: cos_sin must be [>= pos0+tokens, head_size]")
+        if cs.dtype != buf.dtype or cs.stride(1) != 1:
+            cs = cs.to(buf.dtype).contiguous()
+    with torch.cuda.device(buf.device):
+        rc = _lib.load().fdm_qk_norm_rope(buf.data_ptr(), _ptr(wq), _ptr(wk), _ptr(cs), tokens, q_heads, k_heads,
+                                          head_size, buf.stride(0) if tokens > 1 else width, q_offset, k_offset, pos0,
+                                          cs.stride(0) if cs is not None else 0, float(eps),
+                                          1 if across_heads else 0, _dt(buf, what), _stream(buf))
+    _lib.check(rc, what)
+
+
+def qk_norm_rope_(buf, wq, wk, cos_sin, q_heads, k_heads, head_size, q_offset=0, k_offset=None, pos0=0, eps=1e-6,
+                  across_heads=False):
+    """In place on a fused qkv projection [tokens, >= (q_heads+k_heads)*head_size]: rms_norm(q), rms_norm(k)
+    and the interleaved rotary embedding, bit-identical to rms_norm + rotary_pos_embedding."""
+    if k_offset is None:
+        k_offset = q_offset + q_heads * head_size
+    torch.ops.fastdm_b200.qk_norm_rope_(buf, wq, wk, cos_sin, q_heads, k_heads, head_size, q_offset, k_offset, pos0,
+                                        eps, across_heads)
+
+
+@torch.library.custom_op("fastdm_b200::layernorm_modulate_quant", mutates_args=())
+def _ln_mod_quant(x: torch.Tensor, mul: Optional[torch.Tensor], add: Optional[torch.Tensor], rows_per_batch: int,
+                  eps: float, round_steps: bool, out_code: int, want_y: bool
+                  ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    what = "layernorm_modulate_quant"
+    _cuda(x, what)
+    if x.ndim != 2 or x.stride(1) != 1 or x.dtype != torch.bfloat16:
+        raise RuntimeError(f"fastdm_b200.{what}: x must be bf16 [rows, cols] with unit column stride")
+    rows, cols = x.shape
+    for t in (mul, add):
+        if t is not None and (t.dtype != torch.float32 or t.ndim != 2 or t.shape[1] != cols or not t.is_contiguous()
+                              or t.shape[0] * rows_per_batch < rows):
+            raise RuntimeError(f"fastdm_b200.{what}: mul/add must be contiguous float32 [batches, cols] covering all rows")
+    dev = x.device
+    qdt = {FDM_E4M3: torch.float8_e4m3fn, FDM_S8: torch.int8}.get(out_code)
+    q = torch.empty((rows, cols) if qdt is not None else (0, cols), device=dev, dtype=qdt or torch.int8)
+    scale = torch.empty((rows if qdt is not None else 0, 1), device=dev, dtype=torch.float32)
+    azp = torch.empty((rows if out_code == FDM_S8 else 0, 1), device=dev, dtype=torch.int32)
+    y = torch.empty((rows, cols) if want_y else (0, cols), device=dev, dtype=x.dtype)
+    with torch.cuda.device(dev):
+        rc = _lib.load().fdm_layernorm_modulate_quant(
+            x.data_ptr(), _ptr(mul), _ptr(add), q.data_ptr() if qdt is not None else None,
+            scale.data_ptr() if qdt is not None else None, azp.data_ptr() if out_code == FDM_S8 else None,
+            y.data_ptr() if want_y else None, rows, cols, x.stride(0) if rows > 1 else cols, cols,
+            max(rows_per_batch, 1), float(eps), 1 if round_steps else 0, FDM_BF16,
+            out_code if qdt is not None else FDM_BF16, _stream(x))
+    _lib.check(rc, what)
+    return q, scale, azp, y
+
+
+@_ln_mod_quant.register_fake
+def _(x, mul, add, rows_per_batch, eps, round_steps, out_code, want_y):
+    rows, cols = x.shape
+    has_q = out_code in (FDM_E4M3, FDM_S8)
+    return (x.new_empty((rows if has_q else 0, cols), dtype=torch.float8_e4m3fn if out_code == FDM_E4M3 else torch.int8),
+            x.new_empty((rows if has_q else 0, 1), dtype=torch.float32),
+            x.new_empty((rows if out_code == FDM_S8 else 0, 1), dtype=torch.int32),
+            x.new_empty((rows if want_y else 0, cols)))
+
+
+def layernorm_modulate_quant(x, mul, add, rows_per_batch, quant_dtype, eps=1e-6, round_steps=True, want_y=False):
+    """LayerNorm(x) * mul + add (no affine LN) followed by the per-token quantisation the next
+    QLinear would do. Returns (codes, scales, azp-or-None, y-or-None)."""
+    code = {torch.float8_e4m3fn: FDM_E4M3, torch.int8: FDM_S8, None: FDM_BF16}[quant_dtype]
+    q, s, zp, y = torch.ops.fastdm_b200.layernorm_modulate_quant(x, mul, add, rows_per_batch, eps, round_steps, code,
+                                                                 want_y or quant_dtype is None)
+    return (q if quant_dtype is not None else None, s if quant_dtype is not None else None,
+            zp if quant_dtype == torch.int8 else None, y if (want_y or quant_dtype is None) else None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -376,20 +487,36 @@ def quantize_to_fp8(input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def fp8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
-               out_dtype: torch.dtype, bias: Optional[torch.Tensor] = None, act: Optional[str] = None) -> torch.Tensor:
-    """operators_set.py:102-124 (+ optional fused GELU epilogue `act`)."""
+               out_dtype: torch.dtype, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+               out: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+               residual: Optional[torch.Tensor] = None, rows_per_batch: int = 1, round_steps: bool = True
+               ) -> torch.Tensor:
+    """operators_set.py:102-124. Extras beyond the reference signature (all optional): `act` fuses
+    F.gelu into the epilogue, `out` writes into a preallocated (possibly column-sliced) tensor,
+    `gate`/`residual` fold `residual + gate * linear(x)` into the epilogue."""
     if b.shape[0] % 16 or b.shape[1] % 16:  # kernel/cuda/matrixmul.py:31
         raise AssertionError("fp8_matmul: K and N must be multiples of 16")
-    return torch.ops.fastdm_b200.gemm_fp8(a, b, scale_a, scale_b, out_dtype, bias, _ACT[act])
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[1]), device=a.device, dtype=out_dtype)
+    torch.ops.fastdm_b200.gemm_fp8_(out, a, b, scale_a, scale_b, bias, _ACT[act], gate, residual, rows_per_batch,
+                                    round_steps)
+    return out
 
 
 def int8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
                 out_dtype: torch.dtype, azp_adj: Optional[torch.Tensor], azp: Optional[torch.Tensor],
-                bias: Optional[torch.Tensor] = None, act: Optional[str] = None) -> torch.Tensor:
-    """operators_set.py:126-152 (+ optional fused GELU epilogue `act`)."""
+                bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+                out: Optional[torch.Tensor] = None, gate: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None, rows_per_batch: int = 1, round_steps: bool = True
+                ) -> torch.Tensor:
+    """operators_set.py:126-152 (same optional extras as fp8_matmul)."""
     if b.shape[0] % 16 or b.shape[1] % 16:  # kernel/cuda/matrixmul.py:65
         raise AssertionError("int8_matmul: K and N must be multiples of 16")
-    return torch.ops.fastdm_b200.gemm_int8(a, b, scale_a, scale_b, out_dtype, azp_adj, azp, bias, _ACT[act])
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[1]), device=a.device, dtype=out_dtype)
+    torch.ops.fastdm_b200.gemm_int8_(out, a, b, scale_a, scale_b, azp_adj, azp, bias, _ACT[act], gate, residual,
+                                     rows_per_batch, round_steps)
+    return out
 
 
 def scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor, num_q_heads: int,
@@ -402,7 +529,7 @@ def scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, value: 
         raise NotImplementedError("fastdm_b200.scaled_dot_product_attention: GQA/MQA is not on the DiT hot path")
     if scale is None:
         scale = head_dim ** -0.5
-    return torch.ops.fastdm_b200.attn_fwd(query, key, value, num_q_heads, head_dim, scale, None, 128, 64)
+    return attention(query, key, value, num_q_heads, head_dim, scale)
 
 
 def sparse_scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, value: torch.Tensor,
@@ -417,8 +544,7 @@ def sparse_scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, 
         raise NotImplementedError("fastdm_b200.sparse_scaled_dot_product_attention: GQA/MQA unsupported")
     if scale is None:
         scale = head_dim ** -0.5
-    return torch.ops.fastdm_b200.attn_fwd(query, key, value, num_q_heads, head_dim, scale, sparse_mask,
-                                          block_q, block_k)
+    return attention(query, key, value, num_q_heads, head_dim, scale, sparse_mask, block_q, block_k)
 
 
 # fused extras used by the host-side layers (fastdm_b200/layers.py)

@@ -88,6 +88,40 @@ int fdm_rope(void* q, void* k, const void* cos_sin, int64_t batch, int64_t seq, 
              int64_t k_batch_stride, int64_t k_token_stride, int64_t cs_row_stride, int is_neox,
              int dtype, void* stream);
 
+/* Fused q/k RMSNorm + RoPE, in place on a fused qkv projection buffer -- the adjacent ops of
+ * Attention.forward (fastdm/layer/transformer.py:275-298: slice, .contiguous(), rms_norm x2, rope)
+ * and WanAttention.forward (:490-499) in one pass over q and k. Bit-identical to running
+ * fdm_rms_norm then fdm_rope.
+ *   buf      [tokens, ...] rows `token_stride` elements apart; q heads start at column q_offset,
+ *            k heads at column k_offset (v, wherever it is, is untouched)
+ *   across_heads = 0: each head is normalised on its own, wq/wk are [head_size]   (FLUX/SD3/Qwen)
+ *   across_heads = 1: one norm over all q (k) heads of a token, wq/wk are [heads*head_size] (Wan)
+ *   wq / wk  NULL => that tensor is not normalised;  cos_sin NULL => no rotation
+ *   pos0     cache row of token 0 (text tokens precede image tokens in a joint sequence)
+ *   rotation is the interleaved (is_neox = 0) form, the only one on the hot path */
+int fdm_qk_norm_rope(void* buf, const void* wq, const void* wk, const void* cos_sin, int64_t tokens,
+                     int q_heads, int k_heads, int head_size, int64_t token_stride, int64_t q_offset,
+                     int64_t k_offset, int64_t pos0, int64_t cs_row_stride, float eps,
+                     int across_heads, int dtype, void* stream);
+
+/* LayerNorm (no affine, eps) * mul + add, fused with the per-token quantisation of the quantised
+ * linear that consumes it -- the AdaLN "modulate" in front of every qkv / ff1 / proj_mlp GEMM
+ * (SURVEY.md 8(f) item 1).
+ *   round_steps = 1 (FLUX/SD3/Qwen, bf16 tensor ops): y = T(T(T(LN(x)) * mul) + add), mul = T(1+scale)
+ *       fastdm/layer/normalization.py:191-199,228-234; fastdm/model/flux.py:156-158,170-171
+ *   round_steps = 0 (Wan, fp32 chain):              y = T(LN(x) * mul + add)
+ *       fastdm/model/wan.py:95,108 (mul = 1+scale, add = shift) and :101 (mul = weight, add = bias)
+ *   mul / add  fp32 [batches, cols] or NULL; row r uses batch r / rows_per_batch
+ *   out_dtype  FDM_E4M3 -> out + scale[rows]; FDM_S8 -> out + scale + azp (asymmetric);
+ *              anything else -> no quantised output (y_out required)
+ *   y_out      optional bf16 copy of y (row stride y_row_stride), NULL to skip
+ * The quantised codes equal fdm_quant_*(y) bit for bit. */
+int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* add, void* out,
+                                 float* scale, int32_t* azp, void* y_out, int64_t rows, int64_t cols,
+                                 int64_t in_row_stride, int64_t y_row_stride, int64_t rows_per_batch,
+                                 float eps, int round_steps, int in_dtype, int out_dtype,
+                                 void* stream);
+
 /* out[r, :d] = x[r, :d] * gelu_erf(x[r, d:2d])   (second half gated).
  * The reference has no CUDA kernel for this op (fastdm/kernel/cuda/gelumul.py:17 raises; the
  * dispatcher forces Triton, fastdm/kernel/operators_set.py:54). Semantics:
@@ -129,6 +163,22 @@ int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const floa
                   int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd, int out_dtype,
                   int act, void* stream);
 
+/* The same GEMMs with the block's gate / residual chain folded into the epilogue (SURVEY.md 8(f)
+ * item 2): d = T( residual + G ), G = gate[row / rows_per_batch, n] * T(linear) (rounded to T when
+ * round_steps = 1, i.e. bf16 tensor ops: fastdm/model/flux.py:153-154,161-163,69-72; kept in fp32
+ * when round_steps = 0: fastdm/model/wan.py:97,112). gate fp32 [batches, N] or NULL (plain residual
+ * add, wan.py:105); residual [M, N] out_dtype with row stride ldr or NULL; d may alias residual. */
+int fdm_gemm_fp8_residual(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                          const void* bias, void* d, int64_t M, int64_t N, int64_t K, int64_t lda,
+                          int64_t ldb, int64_t ldd, int out_dtype, int act, const float* gate,
+                          const void* residual, int64_t ldr, int64_t rows_per_batch, int round_steps,
+                          void* stream);
+int fdm_gemm_int8_residual(const void* a, const void* b, const float* scale_a, const float* scale_b,
+                           const int32_t* azp_adj, const int32_t* azp, const void* bias, void* d,
+                           int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldd,
+                           int out_dtype, int act, const float* gate, const void* residual,
+                           int64_t ldr, int64_t rows_per_batch, int round_steps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Family 2: attention. Non-causal multi-head attention, token-major ("NHD") layouts.
  * ------------------------------------------------------------------------------------------- */
@@ -139,7 +189,9 @@ int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const floa
  * (csrc/torch_bindings.cpp:162-189). Semantics: fastdm/kernel/torch/attention.py:7-43 and the fp32
  * reference tests/test_attention.py:23-63.
  *   q [B, Sq, H, hd], k/v [B, Sk, H, hd]: element (b,s,h,d) at base + b*batch_stride + s*token_stride + h*hd + d
- *   o [B, Sq, H, hd] contiguous (token stride H*hd), always BF16 (F16 when qkv_dtype is F16)
+ *   o [B, Sq, H, hd] with strides (o_batch_stride, o_token_stride), unit-stride head/dim: may be a
+ *     column slice of a wider buffer (FLUX single block: cat([attn, mlp]) without the cat);
+ *     always BF16 (F16 when qkv_dtype is F16)
  *   qkv_dtype: FDM_BF16 | FDM_F16 | FDM_E4M3 (fp8: per-tensor descale 1.0, P quantised to e4m3
  *              unscaled -- the reference's only fp8 semantics, csrc/attention/interface.cu:262-270)
  *   hd in {64, 128}
@@ -149,8 +201,9 @@ int fdm_gemm_int8(const void* a, const void* b, const float* scale_a, const floa
 int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o, const int8_t* block_mask,
                  int64_t B, int64_t Sq, int64_t Sk, int H, int hd, int64_t q_batch_stride,
                  int64_t q_token_stride, int64_t k_batch_stride, int64_t k_token_stride,
-                 int64_t v_batch_stride, int64_t v_token_stride, int mask_bq, int mask_bk,
-                 float scale, int qkv_dtype, void* stream);
+                 int64_t v_batch_stride, int64_t v_token_stride, int64_t o_batch_stride,
+                 int64_t o_token_stride, int mask_bq, int mask_bk, float scale, int qkv_dtype,
+                 void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Family 4 helpers: Ulysses sequence-parallel layout kernels (no reference counterpart; the

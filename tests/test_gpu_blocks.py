@@ -1,0 +1,199 @@
+"""GPU parity of the fused block path (fastdm_b200/blocks.py, every kernel through the C ABI)
+against (1) the golden block fixtures produced by the REAL reference classes at reduced width and
+(2) the CPU oracle (oracle/blocks_ref.py) at the BASELINE C1 shapes (FLUX block pair, 4096 image +
+512 text tokens, d = 3072, 24 x 128 heads).
+
+Bar (BASELINE.json north_star): cosine >= 0.999 on full-block outputs; we also bound the max abs
+error relative to the output scale. The fused kernels reproduce the reference's rounding chain, so
+the residual differences come from GEMM/attention accumulation order only.
+"""
+import pytest
+import torch
+
+from conftest import golden
+from oracle import blocks_ref as B
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+BF = torch.bfloat16
+
+
+def cosine(a, b):
+    a, b = a.flatten().double().cpu(), b.flatten().double().cpu()
+    return float((a @ b) / (a.norm() * b.norm()))
+
+
+def check(got, want, what, cos_min=0.999, rel=0.05):
+    c = cosine(got, want)
+    err = (got.float().cpu() - want.float()).abs().max().item()
+    scale = want.float().abs().max().item()
+    assert c >= cos_min, f"{what}: cosine {c}"
+    assert err <= rel * scale, f"{what}: max abs err {err} vs scale {scale}"
+    return c
+
+
+def to_dev(sd):
+    return {k: v.to(DEV) for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("tag,quant", [("fp8", torch.float8_e4m3fn), ("int8", torch.int8)])
+def test_flux_blocks_golden(lib, tag, quant):
+    from fastdm_b200.blocks import FluxSingleTransformerBlock, FluxTransformerBlock
+
+    c = golden(f"block_flux_{tag}.pt")
+    blk = FluxTransformerBlock(to_dev(c["sd_double"]), "transformer_blocks.0", c["heads"], c["hd"], quant)
+    enc, hid = blk.forward(c["img"].to(DEV), c["txt"].to(DEV), c["temb"].to(DEV), c["rope"].to(DEV))
+    check(enc, c["enc_out"], "double block / text stream")
+    check(hid, c["hid_out"], "double block / image stream")
+    sblk = FluxSingleTransformerBlock(to_dev(c["sd_single"]), "single_transformer_blocks.0", c["heads"], c["hd"], quant)
+    out = sblk.forward(c["single_in"].to(DEV), c["temb"].to(DEV), c["rope"].to(DEV))
+    check(out, c["single_out"], "single block")
+
+
+@pytest.mark.parametrize("tag,quant", [("fp8", torch.float8_e4m3fn), ("int8", torch.int8)])
+def test_wan_block_golden(lib, tag, quant):
+    from fastdm_b200.blocks import WanTransformerBlock
+
+    c = golden(f"block_wan_{tag}.pt")
+    blk = WanTransformerBlock(to_dev(c["sd"]), "blocks.0", c["heads"], c["hd"], quant)
+    y = blk.forward(c["x"].to(DEV), c["enc"].to(DEV), c["temb"].to(DEV), (c["cos"].to(DEV), c["sin"].to(DEV)))
+    check(y, c["y"], "wan block")
+
+
+def test_qlinear_weight_quant_matches_reference_cpu_quant(lib):
+    # load-time weight quantisation on the GPU == fastdm/utils/quantization.py on the CPU, bit for bit
+    from fastdm_b200.layers import load_linear
+    from oracle.blocks_ref import QLinearRef
+
+    g = torch.Generator().manual_seed(3)
+    sd = {"a.weight": (torch.randn(192, 256, generator=g) * 0.02).to(BF), "a.bias": torch.randn(192, generator=g).to(BF),
+          "b.weight": (torch.randn(64, 256, generator=g) * 0.02).to(BF), "b.bias": torch.randn(64, generator=g).to(BF)}
+    for quant in (torch.float8_e4m3fn, torch.int8):
+        ref = QLinearRef(sd, ["a", "b"], quant)
+        lin = load_linear(to_dev(sd), ["a", "b"], quant)
+        assert torch.equal(lin.weight.cpu().view(torch.uint8), ref.weight.view(torch.uint8))
+        assert torch.equal(lin.weight_quant_scale.cpu(), ref.scale)
+        assert torch.equal(lin.bias.cpu(), ref.bias)
+        if quant == torch.int8:
+            assert torch.equal(lin.weight_asym_sumcol.cpu(), ref.colsum)
+        x = torch.randn(2, 37, 256, generator=g).to(BF)
+        y = lin.forward(x.to(DEV))
+        want = ref.forward(x)
+        assert y.shape == want.shape
+        torch.testing.assert_close(y.cpu().float(), want.float(), rtol=1.6e-2, atol=2e-2 * float(want.float().abs().mean()))
+
+
+def test_fused_norm_rope_equals_separate_ops(lib):
+    from fastdm_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    S, H, hd = 333, 24, 128
+    d = H * hd
+    fused = torch.randn(S, 3 * d, generator=g).to(BF).to(DEV)
+    wq = torch.randn(hd, generator=g).to(BF).to(DEV)
+    wk = torch.randn(hd, generator=g).to(BF).to(DEV)
+    cs = torch.rand(S + 7, hd, generator=g).to(BF).to(DEV)
+    a = fused.clone()
+    ops.qk_norm_rope_(a, wq, wk, cs, H, H, hd, 0, d, 7, 1e-6)
+    q = ops.rms_norm(fused[:, :d].reshape(S, H, hd).contiguous(), wq, 1e-6).view(1, S, d)
+    k = ops.rms_norm(fused[:, d:2 * d].reshape(S, H, hd).contiguous(), wk, 1e-6).view(1, S, d)
+    ops.rotary_pos_embedding(q, k, hd, cs[7:], False)
+    assert torch.equal(a[:, :d], q[0]) and torch.equal(a[:, d:2 * d], k[0]) and torch.equal(a[:, 2 * d:], fused[:, 2 * d:])
+    # Wan: across-heads norm
+    H2 = 40
+    d2 = H2 * hd
+    fused = torch.randn(50, 3 * d2, generator=g).to(BF).to(DEV)
+    wq = torch.randn(d2, generator=g).to(BF).to(DEV)
+    wk = torch.randn(d2, generator=g).to(BF).to(DEV)
+    cs = torch.rand(50, hd, generator=g).to(BF).to(DEV)
+    a = fused.clone()
+    ops.qk_norm_rope_(a, wq, wk, cs, H2, H2, hd, 0, d2, 0, 1e-6, across_heads=True)
+    q = ops.rms_norm(fused[:, :d2].contiguous(), wq, 1e-6).view(1, 50, d2)
+    k = ops.rms_norm(fused[:, d2:2 * d2].contiguous(), wk, 1e-6).view(1, 50, d2)
+    ops.rotary_pos_embedding(q, k, hd, cs, False)
+    assert torch.equal(a[:, :d2], q[0]) and torch.equal(a[:, d2:2 * d2], k[0])
+
+
+def test_layernorm_modulate_quant_equals_unfused(lib):
+    import torch.nn.functional as F
+
+    from fastdm_b200 import ops
+
+    g = torch.Generator().manual_seed(6)
+    Bn, S, d = 2, 300, 3072
+    x = torch.randn(Bn * S, d, generator=g).to(BF).to(DEV)
+    scale = (torch.randn(Bn, d, generator=g) * 0.2).to(BF).to(DEV)
+    shift = (torch.randn(Bn, d, generator=g) * 0.2).to(BF).to(DEV)
+    # FLUX chain (bf16 tensor ops): normalization.py:196
+    want = (F.layer_norm(x.view(Bn, S, d), (d,), None, None, 1e-6) * (1 + scale[:, None]) + shift[:, None]).view(Bn * S, d)
+    q, s, zp, y = ops.layernorm_modulate_quant(x, (1 + scale).float(), shift.float(), S, torch.float8_e4m3fn, 1e-6,
+                                               round_steps=True, want_y=True)
+    diff = (y.view(torch.int16).int() - want.view(torch.int16).int()).abs()
+    assert int(diff.max()) <= 2 and float((diff != 0).float().mean()) < 5e-3
+    rq, rs = ops.quantize_to_fp8(y)
+    assert torch.equal(q.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(s, rs)
+    q8, s8, zp8, _ = ops.layernorm_modulate_quant(x, (1 + scale).float(), shift.float(), S, torch.int8, 1e-6)
+    rq, rs, rzp = ops.quantize_to_int8(y, False)
+    assert torch.equal(q8, rq) and torch.equal(s8, rs) and torch.equal(zp8, rzp)
+    # Wan chain (fp32): wan.py:95
+    sc32, sh32 = scale.float(), shift.float()
+    want = (F.layer_norm(x.view(Bn, S, d).float(), (d,), None, None, 1e-6) * (1 + sc32[:, None]) + sh32[:, None]).to(BF)
+    _, _, _, y = ops.layernorm_modulate_quant(x, 1 + sc32, sh32, S, None, 1e-6, round_steps=False)
+    diff = (y.view(torch.int16).int() - want.view(Bn * S, d).view(torch.int16).int()).abs()
+    assert int(diff.max()) <= 1 and float((diff != 0).float().mean()) < 5e-3
+
+
+def test_gemm_gate_residual_epilogue_equals_unfused(lib):
+    from fastdm_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(8)
+    M, K, N = 700, 1024, 3072
+    a = torch.randn(M, K, device=DEV, generator=g).to(torch.float8_e4m3fn)
+    b = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(torch.float8_e4m3fn).t()
+    sa = torch.rand(M, 1, device=DEV, generator=g) * 0.1
+    sb = torch.rand(N, 1, device=DEV, generator=g)
+    bias = torch.randn(N, device=DEV, generator=g).to(BF)
+    res = torch.randn(M, N, device=DEV, generator=g).to(BF)
+    gate = torch.randn(2, N, device=DEV, generator=g).to(BF)
+    plain = ops.fp8_matmul(a, b, sa, sb, BF, bias)
+    rows_per_batch = 350
+    gfull = gate.repeat_interleave(rows_per_batch, dim=0)
+    want = res + gfull * plain                      # bf16 tensor ops: flux.py:153-154
+    got = ops.fp8_matmul(a, b, sa, sb, BF, bias, gate=gate.float(), residual=res, rows_per_batch=rows_per_batch)
+    assert torch.equal(got, want)
+    want32 = (res.float() + plain * gfull.float()).to(BF)   # wan.py:97
+    got32 = ops.fp8_matmul(a, b, sa, sb, BF, bias, gate=gate.float(), residual=res, rows_per_batch=rows_per_batch,
+                           round_steps=False)
+    assert torch.equal(got32, want32)
+    inplace = res.clone()
+    ops.fp8_matmul(a, b, sa, sb, BF, bias, residual=inplace, out=inplace)   # wan.py:105
+    assert torch.equal(inplace, res + plain)
+
+
+def test_flux_block_pair_full_size_vs_oracle(lib):
+    """BASELINE config C1: 1 double + 1 single FLUX block, 4096 image + 512 text tokens, d = 3072."""
+    from fastdm_b200.blocks import FluxSingleTransformerBlock, FluxTransformerBlock
+
+    dim, heads, hd = 3072, 24, 128
+    g = torch.Generator().manual_seed(21)
+    img = torch.randn(1, 4096, dim, generator=g).to(BF)
+    txt = torch.randn(1, 512, dim, generator=g).to(BF)
+    temb = torch.randn(1, dim, generator=g).to(BF)
+    rope = torch.rand(4608, hd, generator=g).to(BF)
+    sd = B.flux_double_state_dict("transformer_blocks.0", dim, hd, seed=31)
+    sd1 = B.flux_single_state_dict("single_transformer_blocks.0", dim, hd, seed=32)
+    quant = torch.float8_e4m3fn
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref_d = B.FluxTransformerBlockRef(sd, "transformer_blocks.0", heads, hd, quant)
+    enc_r, hid_r = ref_d.forward(img, txt, temb, rope)
+    cat_r = torch.cat([enc_r, hid_r], dim=1)
+    out_r = B.FluxSingleTransformerBlockRef(sd1, "single_transformer_blocks.0", heads, hd, quant).forward(cat_r, temb, rope)
+
+    blk = FluxTransformerBlock(to_dev(sd), "transformer_blocks.0", heads, hd, quant)
+    enc, hid = blk.forward(img.to(DEV), txt.to(DEV), temb.to(DEV), rope.to(DEV))
+    c1 = check(enc, enc_r, "C1 double / text")
+    c2 = check(hid, hid_r, "C1 double / image")
+    sblk = FluxSingleTransformerBlock(to_dev(sd1), "single_transformer_blocks.0", heads, hd, quant)
+    out = sblk.forward(torch.cat([enc, hid], dim=1), temb.to(DEV), rope.to(DEV))
+    c3 = check(out, out_r, "C1 single")
+    print(f"C1 block-pair cosines: text {c1:.6f} image {c2:.6f} single {c3:.6f}")

@@ -129,12 +129,22 @@ def test_quant_dequant_property_full_size(ops):
 
 
 # ------------------------------------------------------------------ rms_norm
-def ulp_close(a, b, max_frac=1e-3):
-    """a, b bf16: every element within 1 bf16 ulp, at most max_frac of them different at all."""
-    a16 = a.cpu().view(torch.int16).int()
-    b16 = b.cpu().view(torch.int16).int()
+def ulp_stats(a, b):
+    a16 = a.cpu().contiguous().view(torch.int16).int()
+    b16 = b.cpu().contiguous().view(torch.int16).int()
     d = (a16 - b16).abs()
-    return int(d.max()) <= 1 and float((d != 0).float().mean()) <= max_frac
+    return int(d.max()), float((d != 0).float().mean())
+
+
+def ulp_close(a, b, max_frac=1e-3, max_ulp=2):
+    """a, b bf16: every element within `max_ulp` bf16 ulps (a 1-ulp difference in an intermediate
+    bf16 rounding can become 2 ulps after the following multiply), at most max_frac of them
+    different at all."""
+    mx, frac = ulp_stats(a, b)
+    ok = mx <= max_ulp and frac <= max_frac
+    if not ok:
+        print(f"ulp_close: max ulp diff {mx}, fraction differing {frac:.2e}")
+    return ok
 
 
 def test_rmsnorm_golden(ops):
