@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- DiT denoise-step latency on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm, 1 GPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...    # Ulysses sequence parallel, N in {2,4,8}
+    python bench.py --impl reference ...                     # reference torch backend on the host CPUs
+
+Workload (config.workload): one transformer forward (= one denoise step of one CFG branch) of
+  wan  : Wan2.2-T2V-A14B, 768x1280x81 frames -> latent [1,16,21,96,160], 80 640 tokens, 40 blocks,
+         d=5120, 40x128 heads, ffn 13824, FP8 per-token x per-channel  (BASELINE configs[4]; default,
+         because it is the one configuration that spans 1-8 GPUs -- Ulysses, strong scaling)
+  flux : FLUX.1-dev, 1024x2048 -> 8192 image + 512 text tokens, 19 double + 38 single blocks, d=3072,
+         24x128 heads, FP8  (BASELINE configs[2]; single GPU; also reported under "flux" at N=1)
+Random-init weights of the named architecture, synthetic latents / prompt embeddings.
+
+A "step" is one full forward: embedders, all blocks, output projection. `value` times it with the
+inputs resident in HBM (CUDA events, max over ranks); `e2e` times the same call from pinned HOST
+buffers including the H2D copies of the step inputs and the D2H read of the predicted latent.
+Activations per step (>= 0.8 GB per tensor for wan, 0.14 GB for flux) exceed the 126 MB L2, so no
+explicit flush is needed between timed iterations (config.l2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WAN = dict(frames=21, height=96, width=160, in_ch=16, text_len=512, text_dim=4096, heads=40, head_dim=128,
+           ffn=13824, layers=40)
+FLUX = dict(img_tokens=8192, txt_tokens=512, heads=24, head_dim=128, double=19, single=38)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.thread = None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle restatement of the reference torch backend on host cores
+# ---------------------------------------------------------------------------------------------------
+class CpuArm:
+    """ONE block of the workload on a token sample with the CPU oracle (oracle/blocks_ref.py, a
+    restatement of fastdm/model/*.py + fastdm/kernel/torch/*), scaled to the full step: token-local
+    work (GEMMs, norms, quant) linearly in tokens, self-attention quadratically (timed on its own,
+    larger, token sample so the x(N/n)^2 scaling is not applied to a noise-level number)."""
+
+    def __init__(self, workload, tokens, threads, attn_tokens=4096):
+        from oracle import blocks_ref as B
+
+        torch.set_num_threads(threads)
+        self.wl, self.tokens, self.attn_tokens = workload, tokens, attn_tokens
+        bf = torch.bfloat16
+        g = torch.Generator().manual_seed(0)
+        quant = torch.float8_e4m3fn
+        if workload == "wan":
+            self.d, self.H, self.hd = WAN["heads"] * WAN["head_dim"], WAN["heads"], WAN["head_dim"]
+            self.full = WAN["frames"] * (WAN["height"] // 2) * (WAN["width"] // 2)
+            sd = B.wan_block_state_dict("blocks.0", self.d, WAN["ffn"], seed=1)
+            self.blk = B.WanTransformerBlockRef(sd, "blocks.0", self.H, self.hd, quant)
+            self.x = torch.randn(1, tokens, self.d, generator=g).to(bf)
+            self.enc = torch.randn(1, WAN["text_len"], self.d, generator=g).to(bf)
+            self.temb = torch.randn(1, 6, self.d, generator=g).to(bf)
+            self.cos = torch.rand(1, tokens, 1, self.hd, generator=g)
+            self.sin = torch.rand(1, tokens, 1, self.hd, generator=g)
+        else:
+            self.d, self.H, self.hd = FLUX["heads"] * FLUX["head_dim"], FLUX["heads"], FLUX["head_dim"]
+            self.full = FLUX["img_tokens"] + FLUX["txt_tokens"]
+            txt = max(16, tokens // 17)
+            sd = B.flux_double_state_dict("transformer_blocks.0", self.d, self.hd, seed=1)
+            sd1 = B.flux_single_state_dict("single_transformer_blocks.0", self.d, self.hd, seed=2)
+            self.dbl = B.FluxTransformerBlockRef(sd, "transformer_blocks.0", self.H, self.hd, quant)
+            self.sgl = B.FluxSingleTransformerBlockRef(sd1, "single_transformer_blocks.0", self.H, self.hd, quant)
+            self.xi = torch.randn(1, tokens - txt, self.d, generator=g).to(bf)
+            self.xt = torch.randn(1, txt, self.d, generator=g).to(bf)
+            self.temb = torch.randn(1, self.d, generator=g).to(bf)
+            self.rope = torch.rand(tokens, self.hd, generator=g).to(bf)
+        self.q_small = torch.randn(1, tokens, self.d, generator=g).to(bf)
+        self.q_big = torch.randn(1, attn_tokens, self.d, generator=g).to(bf)
+
+    def _attn(self, q):
+        from oracle import ops_ref as R
+
+        t0 = time.perf_counter()
+        R.scaled_dot_product_attention(q, q, q, self.H, self.H, self.hd, scale=self.hd ** -0.5)
+        return time.perf_counter() - t0
+
+    def step(self):
+        """-> (estimated full-step milliseconds, description of the sample)"""
+        t_small, t_big = self._attn(self.q_small), self._attn(self.q_big)
+        r, ra = self.full / self.tokens, self.full / self.attn_tokens
+        if self.wl == "wan":
+            t0 = time.perf_counter()
+            self.blk.forward(self.x, self.enc, self.temb, (self.cos, self.sin))
+            t_block = time.perf_counter() - t0
+            est = WAN["layers"] * (max(t_block - t_small, 0.0) * r + t_big * ra * ra)
+            sample = (f"1 of 40 Wan2.2 blocks (d=5120, ffn 13824, fp8 W8A8) on {self.tokens} of {self.full} tokens + 512 text "
+                      f"tokens: {t_block:.2f} s; self-attention timed on {self.attn_tokens} tokens: {t_big:.2f} s; step = 40 x "
+                      f"(token-local x{r:.1f} + attention x{ra * ra:.0f})")
+        else:
+            t0 = time.perf_counter()
+            e, h = self.dbl.forward(self.xi, self.xt, self.temb, self.rope)
+            t_d = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            self.sgl.forward(torch.cat([e, h], 1), self.temb, self.rope)
+            t_s = time.perf_counter() - t0
+            est = (FLUX["double"] * max(t_d - t_small, 0.0) + FLUX["single"] * max(t_s - t_small, 0.0)) * r \
+                + (FLUX["double"] + FLUX["single"]) * t_big * ra * ra
+            sample = (f"1 double + 1 single FLUX block (d=3072, fp8 W8A8) on {self.tokens} of {self.full} tokens: {t_d:.2f} s + "
+                      f"{t_s:.2f} s; attention timed on {self.attn_tokens} tokens: {t_big:.2f} s; step = 19 double + 38 single "
+                      f"(token-local x{r:.1f} + attention x{ra * ra:.1f})")
+        return est * 1e3, sample
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (its torch backend,
+    restated in oracle/ -- the reference itself is not on the GPU box), all host threads."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    wl = args.workload if args.workload != "auto" else "wan"
+    arm = CpuArm(wl, args.cpu_tokens, threads)
+    vals, sample = [], ""
+    for i in range(args.warmup + args.steps):
+        ms, sample = arm.step()
+        if i >= args.warmup:
+            vals.append(ms)
+    v = sum(vals) / len(vals)
+    line = dict(metric="dit_denoise_step_ms", value=v, unit="ms", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=v, higher_is_better=False, scaling="strong" if wl == "wan" else "weak", vs_baseline=None,
+                dtype="fp8_e4m3 codes, f32 arithmetic on the CPU", data="synthetic", impl="reference",
+                config=workload_config(wl, 1),
+                cpu_baseline=dict(value=v, unit="ms", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=v, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(wl, n):
+    if wl == "wan":
+        return dict(workload="Wan2.2-T2V-A14B one expert transformer forward, 768x1280x81f (latent 1x16x21x96x160, 80640 tokens, "
+                             "40 blocks, d=5120, 40x128 heads, ffn 13824), FP8 per-token x per-channel W8A8, bf16 attention, "
+                             "random-init weights",
+                    parallelism=f"ulysses-sp{n}" if n > 1 else "single-gpu", l2="per-step activations (>=0.8 GB each) exceed the 126 MB L2; no flush")
+    return dict(workload="FLUX.1-dev full transformer forward, 1024x2048 (8192 image + 512 text tokens, 19 double + 38 single "
+                         "blocks, d=3072, 24x128 heads), FP8 per-token x per-channel W8A8, bf16 attention, random-init weights",
+                parallelism="single-gpu" if n == 1 else f"replicas x{n}", l2="per-step activations (0.14 GB each) exceed the 126 MB L2; no flush")
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def build_wan(device, layers):
+    from fastdm_b200.models import WanTransformer3DModelCore
+
+    model = WanTransformer3DModelCore(num_attention_heads=WAN["heads"], attention_head_dim=WAN["head_dim"],
+                                      in_channels=WAN["in_ch"], text_dim=WAN["text_dim"], ffn_dim=WAN["ffn"],
+                                      num_layers=layers, device=device, seed=0)
+    g = torch.Generator().manual_seed(1)
+    host = dict(latent=torch.rand(1, WAN["in_ch"], WAN["frames"], WAN["height"], WAN["width"], generator=g).to(torch.bfloat16).pin_memory(),
+                timestep=torch.tensor([999], dtype=torch.int64).pin_memory(),
+                prompt=torch.rand(1, WAN["text_len"], WAN["text_dim"], generator=g).to(torch.bfloat16).pin_memory())
+    return model, host
+
+
+def build_flux(device, double, single):
+    from fastdm_b200.models import FluxTransformer2DModelCore
+
+    model = FluxTransformer2DModelCore(num_layers=double, num_single_layers=single, device=device, seed=0)
+    g = torch.Generator().manual_seed(1)
+    bf = torch.bfloat16
+    host = dict(latent=torch.rand(1, FLUX["img_tokens"], 64, generator=g).to(bf).pin_memory(),
+                prompt=torch.rand(1, FLUX["txt_tokens"], 4096, generator=g).to(bf).pin_memory(),
+                pooled=torch.rand(1, 768, generator=g).to(bf).pin_memory(),
+                timestep=torch.tensor([1.0]).to(bf).pin_memory(), guidance=torch.tensor([3.5]).to(bf).pin_memory(),
+                img_ids=torch.zeros(FLUX["img_tokens"], 3).pin_memory(), txt_ids=torch.zeros(FLUX["txt_tokens"], 3).pin_memory())
+    return model, host
+
+
+def to_device(host, device):
+    return {k: v.to(device, non_blocking=True) for k, v in host.items()}
+
+
+def step_fn(wl, model, ulysses):
+    if wl == "wan":
+        return lambda d: model.forward(d["latent"], d["timestep"], d["prompt"], ulysses=ulysses)[0]
+    return lambda d: model.forward(d["latent"], d["prompt"], d["pooled"], d["timestep"], d["img_ids"], d["txt_ids"], d["guidance"])[0]
+
+
+def timed_steps(fn, dev_inputs, steps, warmup, world, device):
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        fn(dev_inputs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn(dev_inputs)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def timed_e2e(fn, host, steps, world, device):
+    """Same step from pinned host buffers: H2D of the step inputs + D2H of the predicted latent inside the timed region."""
+    import torch.distributed as dist
+
+    out_host = None
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        d = to_device(host, device)
+        y = fn(d)
+        out_host = y.to("cpu", non_blocking=False)
+    torch.cuda.synchronize()
+    ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / steps], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = out_host.numel() * out_host.element_size()
+    return float(ms.item()), h2d, d2h
+
+
+def attention_roofline(wl, world, device, pk):
+    """The dominant kernel (self-attention: 73% of Wan flops, 32% of FLUX) timed live on its own:
+    CUDA events on the launching stream, algorithmic flops 4*B*H*Sq*Sk*hd per launch."""
+    from fastdm_b200 import ops
+
+    if wl == "wan":
+        S = WAN["frames"] * (WAN["height"] // 2) * (WAN["width"] // 2)
+        H, hd = WAN["heads"] // world, WAN["head_dim"]
+    else:
+        S, H, hd = FLUX["img_tokens"] + FLUX["txt_tokens"], FLUX["heads"], FLUX["head_dim"]
+    qkv = torch.randn(1, S, 3 * H * hd, device=device, dtype=torch.bfloat16)
+    d = H * hd
+    run = lambda: ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd)  # noqa: E731
+    run()
+    torch.cuda.synchronize()
+    n = 3 if wl == "wan" else 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    flops = 4.0 * H * S * S * hd
+    ach = flops / ms / 1e9
+    return dict(bound="tensor", kernel="attn_fwd_kernel<128,bf16>", achieved=ach, peak=pk["bf16"], unit="TFLOP/s",
+                frac=ach / pk["bf16"], traffic=None, ms_per_launch=ms, flops_per_launch=flops,
+                peak_source=pk["src"] + ", bf16 burst (kernel timed alone)")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "wan", "flux"])
+    ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (the JSON line then says so and is not a valid result)")
+    ap.add_argument("--cpu-tokens", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flux", action="store_true", help="skip the secondary FLUX numbers at N=1")
+    ap.add_argument("--no-overlap", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3 and not args.layers:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference for the CPU arm)")
+    import torch.distributed as dist
+
+    from fastdm_b200 import _lib
+    from fastdm_b200.ulysses import UlyssesAttention
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    wl = "wan" if args.workload == "auto" else args.workload
+    if wl == "flux" and world > 1:
+        pass  # replicas: every rank runs the same step, no collective (FLUX stays single-GPU)
+    pk = peaks()
+    _lib.load()
+
+    if wl == "wan":
+        layers = args.layers or WAN["layers"]
+        model, host = build_wan(device, layers)
+        ulysses = UlyssesAttention(WAN["heads"], WAN["head_dim"]) if world > 1 else None
+    else:
+        layers = args.layers or (FLUX["double"] + FLUX["single"])
+        model, host = build_flux(device, args.layers or FLUX["double"], args.layers or FLUX["single"])
+        ulysses = None
+    fn0 = step_fn(wl, model, ulysses)
+    if ulysses is not None and args.no_overlap:
+        fn = lambda d: model.forward(d["latent"], d["timestep"], d["prompt"], ulysses=ulysses, overlap=False)[0]  # noqa: E731
+    else:
+        fn = fn0
+    dev_inputs = to_device(host, device)
+    torch.cuda.synchronize()
+
+    with ClockSampler(local_rank) as clocks:
+        c0 = _lib.launch_count
+        ms = timed_steps(fn, dev_inputs, args.steps, args.warmup, world, device)
+        launches = (_lib.launch_count - c0) // (args.steps + args.warmup)
+    e2e_ms, h2d, d2h = timed_e2e(fn, host, max(1, min(args.steps, 3)), world, device)
+
+    extra = {}
+    if ulysses is not None:
+        # exposed all-to-all time = step time - step time with the exchange replaced by a local copy
+        ulysses.stub_comm = True
+        ms_stub = timed_steps(fn, dev_inputs, max(1, min(args.steps, 2)), 1, world, device)
+        ulysses.stub_comm = False
+        extra["a2a_exposed_ms"] = ms - ms_stub
+        extra["ms_per_step_comm_stubbed"] = ms_stub
+    roof = attention_roofline(wl, world, device, pk)
+
+    if rank == 0 and wl == "wan" and world == 1 and not args.no_flux and not args.layers:
+        del model
+        torch.cuda.empty_cache()
+        fmodel, fhost = build_flux(device, FLUX["double"], FLUX["single"])
+        ffn = step_fn("flux", fmodel, None)
+        fms = timed_steps(ffn, to_device(fhost, device), 10, 3, 1, device)
+        fe2e, fh2d, fd2h = timed_e2e(ffn, fhost, 5, 1, device)
+        froof = attention_roofline("flux", 1, device, pk)
+        extra["flux"] = dict(config=workload_config("flux", 1), ms_per_step=fms, e2e_ms=fe2e, h2d_bytes_per_step=fh2d,
+                             d2h_bytes_per_step=fd2h, attention_tflops=froof["achieved"],
+                             step_tflops=165.4e3 / fms)
+        del fmodel
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, sample = CpuArm(wl, args.cpu_tokens, threads).step()
+        cpu = dict(value=v, unit="ms", cores=threads, kind="port", sample=sample)
+    cfg = workload_config(wl, world)
+    if args.layers:
+        cfg["INVALID_debug_layers"] = args.layers
+    step_tflop = 7291.0 if wl == "wan" else 165.4
+    line = dict(metric="dit_denoise_step_ms", value=ms, unit="ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=False, scaling="strong" if wl == "wan" else "weak", vs_baseline=None,
+                dtype="fp8_e4m3 GEMM (f32 accumulate), bf16 attention (f32 accumulate)", data="synthetic", config=cfg,
+                clocks=clocks.summary(),
+                e2e=dict(value=e2e_ms, unit="ms", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+                gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                step_tflops_per_s=step_tflop * 1e3 / ms, **extra)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -43,8 +43,8 @@ SIGNATURES = {
     "fdm_layernorm_modulate_quant": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_float,
                                              c_int, c_int, c_int, c_void_p]),
-    "fdm_ulysses_pack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p]),
-    "fdm_ulysses_unpack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int64, c_int, c_void_p]),
+    "fdm_ulysses_pack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
+    "fdm_ulysses_unpack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
 }
 
 # dtype / activation enums of the header
@@ -78,7 +78,13 @@ def last_error() -> str:
     return msg.decode("utf-8", "replace") if msg else ""
 
 
+# every C-ABI compute call launches exactly one kernel of ours; bench.py reads this counter
+launch_count = 0
+
+
 def check(rc: int, what: str):
+    global launch_count
+    launch_count += 1
     if rc != 0:
         kind = {-1: "invalid argument", -2: "unsupported device", -3: "CUDA failure", -4: "unsupported"}.get(rc, "error")
         exc = NotImplementedError if rc in (-2, -4) else RuntimeError

@@ -194,9 +194,26 @@ class WanTransformerBlock:
                               across_heads=True)
         return qkv
 
+    def _qkv_group(self, g: int) -> QLinear:
+        """Column group g (0 = q, 1 = k, 2 = v) of the fused qkv projection, sharing its storage."""
+        if not hasattr(self, "_groups"):
+            self._groups = []
+            d = self.dim
+            for i in range(3):
+                lin = QLinear(self.qkv.in_features, d, bias=self.qkv.bias is not None, data_type=self.qkv.dtype,
+                              device_type=self.qkv.device)
+                lin.weight = self.qkv.weight[:, i * d:(i + 1) * d]
+                lin.weight_quant_scale = self.qkv.weight_quant_scale[i * d:(i + 1) * d]
+                if self.qkv.weight_asym_sumcol is not None:
+                    lin.weight_asym_sumcol = self.qkv.weight_asym_sumcol[:, i * d:(i + 1) * d].contiguous()
+                lin.bias = None if self.qkv.bias is None else self.qkv.bias[i * d:(i + 1) * d]
+                self._groups.append(lin)
+        return self._groups[g]
+
     def forward(self, hidden_states, encoder_hidden_states, temb, rotary_emb, sparse_mask=None,
-                block_q=128, block_k=64, attention_fn=None):
-        """attention_fn(qkv [B,S,3d]) -> [B,S,d] lets the Ulysses wrapper replace the local attention."""
+                block_q=128, block_k=64, ulysses=None, pos0=0, overlap=True):
+        """`ulysses` (fastdm_b200.ulysses.UlyssesAttention): hidden_states is this rank's token shard,
+        `pos0` its first position in the full sequence; `rotary_emb` covers the full sequence."""
         B, S, d = hidden_states.shape
         H, hd, qt = self.heads, self.hd, self.quant_type
         shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = (
@@ -208,12 +225,27 @@ class WanTransformerBlock:
         # 1. self-attention: (norm1(x) * (1 + scale) + shift) in fp32, one rounding (wan.py:95)
         xq = Quantized(*ops.layernorm_modulate_quant(hid2, r2(1 + scale_msa), r2(shift_msa), S, qt, self.eps,
                                                      round_steps=False)[:3])
-        qkv = self.self_attention_qkv(xq, B, S, rope_table)
-        if attention_fn is not None:
-            attn = attention_fn(qkv)
-        else:
+        if ulysses is None or ulysses.P == 1:
+            qkv = self.self_attention_qkv(xq, B, S, rope_table, pos0)
             attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale,
                                  sparse_mask, block_q, block_k)
+        elif overlap:
+            norm_w = (self.norm_q1, self.norm_k1, None)
+
+            def group(g):
+                def run():
+                    x = self._qkv_group(g).forward(xq)
+                    if g < 2:
+                        ops.qk_norm_rope_(x, norm_w[g], None, rope_table, H, 0, hd, 0, 0, pos0, self.eps,
+                                          across_heads=True)
+                    return x
+                return run
+
+            attn = ulysses.qkv_projection_overlapped([group(0), group(1), group(2)], self.scale, sparse_mask,
+                                                     block_q, block_k)
+        else:
+            qkv = self.self_attention_qkv(xq, B, S, rope_table, pos0)
+            attn = ulysses.attention(qkv, self.scale, sparse_mask, block_q, block_k)
         h1 = torch.empty_like(hid2)
         # hidden = (hidden.float() + attn_out * gate).type_as(hidden)      (wan.py:97)
         self.to_out1.forward(quantize(attn.view(B * S, d), qt), gate=r2(gate_msa), residual=hid2, rows_per_batch=S,

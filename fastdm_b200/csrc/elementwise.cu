@@ -854,24 +854,29 @@ __global__ void __launch_bounds__(512) ln_mod_quant_kernel(
 template <bool PACK>
 __global__ void __launch_bounds__(256) ulysses_heads_kernel(const uint8_t* __restrict__ src,
                                                             uint8_t* __restrict__ dst,
-                                                            int64_t S, int H, int P,
+                                                            int64_t S, int H, int P, int n_seg,
                                                             int64_t head_bytes,
-                                                            int64_t token_stride_bytes) {
-  // PACK:   src token-major strided [S, H*head_bytes], dst [P, S, (H/P)*head_bytes]
-  // !PACK:  src [P, S, (H/P)*head_bytes], dst token-major strided
+                                                            int64_t token_stride_bytes,
+                                                            int64_t seg_stride_bytes) {
+  // strided side : token-major [S, n_seg segments (q|k|v) of H heads], rows token_stride_bytes apart,
+  //                segments seg_stride_bytes apart
+  // packed side  : [P, S, n_seg, H/P, head] -- chunk p holds head group p of every segment
+  // PACK copies strided -> packed, !PACK packed -> strided.
   const int hp = H / P;
   const int64_t vec_per_head = head_bytes >> 4;
-  const int64_t vec_per_tok = (int64_t)H * vec_per_head;
+  const int64_t vec_per_tok = (int64_t)n_seg * H * vec_per_head;
   const int64_t total = S * vec_per_tok;
   for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < total;
        it += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = it / vec_per_tok;
-    const int64_t rem = it - s * vec_per_tok;
+    int64_t rem = it - s * vec_per_tok;
+    const int seg = (int)(rem / ((int64_t)H * vec_per_head));
+    rem -= (int64_t)seg * H * vec_per_head;
     const int h = (int)(rem / vec_per_head);
     const int64_t v = rem - (int64_t)h * vec_per_head;
     const int p = h / hp, hl = h - p * hp;
-    const int64_t strided = s * token_stride_bytes + (int64_t)h * head_bytes + v * 16;
-    const int64_t packed = (((int64_t)p * S + s) * hp + hl) * head_bytes + v * 16;
+    const int64_t strided = s * token_stride_bytes + seg * seg_stride_bytes + (int64_t)h * head_bytes + v * 16;
+    const int64_t packed = ((((int64_t)p * S + s) * n_seg + seg) * hp + hl) * head_bytes + v * 16;
     if (PACK) stg128(dst + packed, ldg128_stream(src + strided));
     else stg128(dst + strided, ldg128_stream(src + packed));
   }
@@ -1156,40 +1161,48 @@ int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* 
   return FDM_OK;
 }
 
-static int ulysses_common(const void* src, void* dst, int64_t S, int H, int hd, int P,
-                          int64_t token_stride, int elem_size, bool pack, void* stream) {
+static int ulysses_common(const void* src, void* dst, int64_t S, int H, int hd, int P, int n_seg,
+                          int64_t token_stride, int64_t seg_stride, int elem_size, bool pack,
+                          void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  FDM_REQUIRE(S >= 0 && H > 0 && hd > 0 && P > 0, "ulysses: bad shape");
+  FDM_REQUIRE(S >= 0 && H > 0 && hd > 0 && P > 0 && n_seg > 0, "ulysses: bad shape");
   FDM_REQUIRE(H % P == 0, "ulysses: heads (%d) not divisible by ranks (%d)", H, P);
   FDM_REQUIRE(elem_size == 1 || elem_size == 2 || elem_size == 4, "ulysses: elem_size");
   const int64_t head_bytes = (int64_t)hd * elem_size;
-  FDM_REQUIRE(head_bytes % 16 == 0 && (token_stride * elem_size) % 16 == 0,
-              "ulysses: head / token stride must be multiples of 16 bytes");
+  FDM_REQUIRE(head_bytes % 16 == 0 && (token_stride * elem_size) % 16 == 0 &&
+                  (seg_stride * elem_size) % 16 == 0,
+              "ulysses: head / token / segment strides must be multiples of 16 bytes");
   FDM_REQUIRE((uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "ulysses: alignment");
   if (S == 0) return FDM_OK;
   FDM_REQUIRE(src && dst, "ulysses: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t total = S * H * (head_bytes / 16);
+  const int64_t total = S * n_seg * H * (head_bytes / 16);
   const unsigned g = grid_for(total, 256);
   if (pack)
-    ulysses_heads_kernel<true><<<g, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, S, H, P,
-                                                  head_bytes, token_stride * elem_size);
+    ulysses_heads_kernel<true><<<g, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, S, H, P, n_seg,
+                                                  head_bytes, token_stride * elem_size,
+                                                  seg_stride * elem_size);
   else
-    ulysses_heads_kernel<false><<<g, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, S, H, P,
-                                                   head_bytes, token_stride * elem_size);
+    ulysses_heads_kernel<false><<<g, 256, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, S, H, P, n_seg,
+                                                   head_bytes, token_stride * elem_size,
+                                                   seg_stride * elem_size);
   FDM_LAUNCH_CHECK("ulysses layout kernel launch");
   return FDM_OK;
 }
 
 int fdm_ulysses_pack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
-                           int64_t src_token_stride, int elem_size, void* stream) {
-  return ulysses_common(src, dst, S_local, H, hd, P, src_token_stride, elem_size, true, stream);
+                           int n_seg, int64_t src_token_stride, int64_t src_seg_stride,
+                           int elem_size, void* stream) {
+  return ulysses_common(src, dst, S_local, H, hd, P, n_seg, src_token_stride, src_seg_stride,
+                        elem_size, true, stream);
 }
 
 int fdm_ulysses_unpack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
-                             int64_t dst_token_stride, int elem_size, void* stream) {
-  return ulysses_common(src, dst, S_local, H, hd, P, dst_token_stride, elem_size, false, stream);
+                             int n_seg, int64_t dst_token_stride, int64_t dst_seg_stride,
+                             int elem_size, void* stream) {
+  return ulysses_common(src, dst, S_local, H, hd, P, n_seg, dst_token_stride, dst_seg_stride,
+                        elem_size, false, stream);
 }
 
 }  // extern "C"

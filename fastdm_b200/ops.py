@@ -423,33 +423,35 @@ def layernorm_modulate_quant(x, mul, add, rows_per_batch, quant_dtype, eps=1e-6,
 # ------------------------------------------------------------------------------------------------
 # Ulysses layout helpers
 # ------------------------------------------------------------------------------------------------
-def ulysses_pack_heads(x: torch.Tensor, num_heads: int, world: int) -> torch.Tensor:
-    """[S, H*hd] (row stride free) -> [P, S, H/P * hd] contiguous send buffer."""
+def ulysses_pack_heads(x: torch.Tensor, num_heads: int, head_dim: int, world: int, n_seg: int = 1) -> torch.Tensor:
+    """x [S, >= n_seg*H*hd] (n_seg head-major segments side by side, e.g. a fused qkv projection)
+    -> send buffer [P, S, n_seg * (H/P) * hd]: chunk p = head group p of every segment."""
     _cuda(x, "ulysses_pack_heads")
-    s, c = x.shape
-    hd = c // num_heads
+    s = x.shape[0]
+    c = num_heads * head_dim
     if x.stride(1) != 1:
         x = x.contiguous()
-    out = torch.empty((world, s, c // world), device=x.device, dtype=x.dtype)
+    out = torch.empty((world, s, n_seg * c // world), device=x.device, dtype=x.dtype)
     with torch.cuda.device(x.device):
-        rc = _lib.load().fdm_ulysses_pack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, hd, world,
-                                                x.stride(0) if s > 1 else c, x.element_size(), _stream(x))
+        rc = _lib.load().fdm_ulysses_pack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, head_dim, world, n_seg,
+                                                x.stride(0) if s > 1 else x.shape[1], c, x.element_size(), _stream(x))
     _lib.check(rc, "ulysses_pack_heads")
     return out
 
 
-def ulysses_unpack_heads(x: torch.Tensor, num_heads: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """[P, S, H/P * hd] received chunks -> [S, H*hd]."""
+def ulysses_unpack_heads(x: torch.Tensor, num_heads: int, head_dim: int, n_seg: int = 1,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [P, S, n_seg * (H/P) * hd] (chunk p = head group p) -> [S, n_seg * H * hd]."""
     _cuda(x, "ulysses_unpack_heads")
-    world, s, cp = x.shape
-    c = cp * world
-    hd = c // num_heads
+    world, s, _ = x.shape
+    c = num_heads * head_dim
     x = x.contiguous()
     if out is None:
-        out = torch.empty((s, c), device=x.device, dtype=x.dtype)
+        out = torch.empty((s, n_seg * c), device=x.device, dtype=x.dtype)
     with torch.cuda.device(x.device):
-        rc = _lib.load().fdm_ulysses_unpack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, hd, world,
-                                                  out.stride(0) if s > 1 else c, x.element_size(), _stream(x))
+        rc = _lib.load().fdm_ulysses_unpack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, head_dim, world, n_seg,
+                                                  out.stride(0) if s > 1 else out.shape[1], c, x.element_size(),
+                                                  _stream(x))
     _lib.check(rc, "ulysses_unpack_heads")
     return out
 

@@ -210,16 +210,21 @@ int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o, const int
  * exchange itself is NCCL all-to-all issued from the host side, fastdm_b200/ulysses.py).
  * ------------------------------------------------------------------------------------------- */
 
-/* Pack src [S_local, H, hd] (token stride src_token_stride) into dst [P, S_local, H/P, hd]
- * contiguous, i.e. chunk p holds heads [p*H/P, (p+1)*H/P): the send buffer of the pre-attention
- * all-to-all. elem_size in bytes (1, 2 or 4); H % P == 0. */
+/* Pack the local token shard of n_seg head-major tensors (e.g. the q|k|v segments of a fused qkv
+ * projection: n_seg = 3, segments src_seg_stride elements apart, rows src_token_stride apart) into
+ * the send buffer of the pre-attention all-to-all: dst [P, S_local, n_seg, H/P, hd] contiguous,
+ * chunk p = head group p of every segment. After the exchange the receive buffer IS
+ * [P*S_local tokens, n_seg, H/P, hd] -- the full sequence for this rank's heads, ready for
+ * fdm_attn_fwd with token stride n_seg*(H/P)*hd. elem_size in bytes (1, 2, 4); H % P == 0. */
 int fdm_ulysses_pack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
-                           int64_t src_token_stride, int elem_size, void* stream);
+                           int n_seg, int64_t src_token_stride, int64_t src_seg_stride,
+                           int elem_size, void* stream);
 
-/* Inverse of the above for the post-attention all-to-all: src [P, S_local, H/P, hd] (received
- * chunks, chunk p = heads of rank p) -> dst [S_local, H, hd] with token stride dst_token_stride. */
+/* Inverse, for the post-attention all-to-all: src [P, S_local, n_seg, H/P, hd] (chunk p = head
+ * group p, received from rank p) -> dst token-major [S_local, n_seg x (H, hd)]. */
 int fdm_ulysses_unpack_heads(const void* src, void* dst, int64_t S_local, int H, int hd, int P,
-                             int64_t dst_token_stride, int elem_size, void* stream);
+                             int n_seg, int64_t dst_token_stride, int64_t dst_seg_stride,
+                             int elem_size, void* stream);
 
 #ifdef __cplusplus
 }

@@ -128,8 +128,10 @@ def test_layernorm_modulate_quant_equals_unfused(lib):
     want = (F.layer_norm(x.view(Bn, S, d), (d,), None, None, 1e-6) * (1 + scale[:, None]) + shift[:, None]).view(Bn * S, d)
     q, s, zp, y = ops.layernorm_modulate_quant(x, (1 + scale).float(), shift.float(), S, torch.float8_e4m3fn, 1e-6,
                                                round_steps=True, want_y=True)
-    diff = (y.view(torch.int16).int() - want.view(torch.int16).int()).abs()
-    assert int(diff.max()) <= 2 and float((diff != 0).float().mean()) < 5e-3
+    # a 1-ulp difference in LN(x) (|LN| up to ~4 -> ulp 2^-6) survives the modulate even where the result
+    # cancels to ~0, so the bound is absolute: 2 ulps of the largest intermediate; almost all elements equal
+    assert float((y.float() - want.float()).abs().max()) <= 0.07
+    assert float((y != want).float().mean()) < 5e-3
     rq, rs = ops.quantize_to_fp8(y)
     assert torch.equal(q.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(s, rs)
     q8, s8, zp8, _ = ops.layernorm_modulate_quant(x, (1 + scale).float(), shift.float(), S, torch.int8, 1e-6)
@@ -139,8 +141,9 @@ def test_layernorm_modulate_quant_equals_unfused(lib):
     sc32, sh32 = scale.float(), shift.float()
     want = (F.layer_norm(x.view(Bn, S, d).float(), (d,), None, None, 1e-6) * (1 + sc32[:, None]) + sh32[:, None]).to(BF)
     _, _, _, y = ops.layernorm_modulate_quant(x, 1 + sc32, sh32, S, None, 1e-6, round_steps=False)
-    diff = (y.view(torch.int16).int() - want.view(Bn * S, d).view(torch.int16).int()).abs()
-    assert int(diff.max()) <= 1 and float((diff != 0).float().mean()) < 5e-3
+    want = want.view(Bn * S, d)
+    assert float((y.float() - want.float()).abs().max()) <= 0.04   # one rounding: 1 ulp at magnitude < 8
+    assert float((y != want).float().mean()) < 5e-3
 
 
 def test_gemm_gate_residual_epilogue_equals_unfused(lib):
