@@ -246,11 +246,17 @@ def timed_steps(fn, dev_inputs, steps, warmup, world, device):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = os.environ.get("FDM_BENCH_PROFILE") == "1"   # ncu --profile-from-start off: capture only the timed steps
+    if prof:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(steps):
         fn(dev_inputs)
     e1.record()
     torch.cuda.synchronize()
+    if prof:
+        torch.cuda.profiler.stop()
+        os.environ["FDM_BENCH_PROFILE"] = "0"
     if world > 1:
         dist.barrier()
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)

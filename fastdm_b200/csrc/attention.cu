@@ -28,12 +28,14 @@
 // Semantics: fastdm/kernel/torch/attention.py:7-43 (F.scaled_dot_product_attention, non-causal),
 // checked against the fp32 reference of tests/test_attention.py:23-63 at atol 1.8e-2 (:94).
 // Replaces the library routes of fastdm/kernel/cuda/attention.py:149-261.
+#include <stdlib.h>
+
 #include "sm100.cuh"
 
 namespace fdm {
 using namespace sm100;
 
-constexpr int kAttnThreads = 320;
+constexpr int kAttnThreads = 384;  // 2 softmax warpgroups + 1 warpgroup hosting the TMA and MMA warps
 constexpr int kQTile = 128;   // rows per Q tile (UMMA M)
 constexpr int kKvTile = 128;  // keys per KV tile (UMMA N of QK^T, K extent of PV)
 constexpr int kMaxKvTiles = 8192;
@@ -73,7 +75,76 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
 }
 
-template <int HD, bool F16>
+// per-warpgroup register re-budgeting (the kernel is launched at 168 regs/thread = 65536 / 384)
+template <int N>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// ---- packed 2 x fp32 arithmetic (sm_100: FFMA2 / FADD2) and 3-input max -------------------------
+__device__ __forceinline__ uint64_t f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unf2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// max over 32 fp32 values held as raw bits, as a shallow tree (one softmax warp per scheduler is
+// active at a time, so instruction-level parallelism is all the latency hiding there is)
+__device__ __forceinline__ float max32(const uint32_t (&r)[32]) {
+  float m[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    m[i] = fmax3(__uint_as_float(r[3 * i]), __uint_as_float(r[3 * i + 1]), __uint_as_float(r[3 * i + 2]));
+  m[10] = fmaxf(__uint_as_float(r[30]), __uint_as_float(r[31]));
+  const float a = fmax3(m[0], m[1], m[2]), b = fmax3(m[3], m[4], m[5]), c = fmax3(m[6], m[7], m[8]);
+  return fmax3(fmax3(a, b, c), m[9], m[10]);
+}
+// 2^x for a pair on the FMA pipe instead of MUFU: round-to-nearest split x = n + f, f in [-.5,.5],
+// degree-3 minimax polynomial for 2^f (max rel. error 7.5e-5, far below the bf16 rounding of P),
+// exponent patched in with an integer add. Takes load off the 16-op/clk/SM MUFU unit, which is
+// otherwise exactly as busy as the tensor cores for hd = 128 attention.
+__device__ __forceinline__ void ex2_emulated_pair(uint64_t y, float& p0, float& p1) {
+  float y0, y1;
+  unf2(y, y0, y1);
+  y = f2(fmaxf(y0, -126.f), fmaxf(y1, -126.f));
+  const uint64_t kMagic = f2(12582912.f, 12582912.f);      // 1.5 * 2^23
+  const uint64_t kNegMagic = f2(-12582912.f, -12582912.f);
+  const uint64_t kNegOne = f2(-1.f, -1.f);
+  const uint64_t t = fadd2(y, kMagic);                      // round(y) in the low mantissa bits
+  const uint64_t n = fadd2(t, kNegMagic);
+  const uint64_t f = ffma2(n, kNegOne, y);                  // y - round(y)
+  uint64_t q = ffma2(f, f2(0.05517186224460602f, 0.05517186224460602f), f2(0.2426111400127411f, 0.2426111400127411f));
+  q = ffma2(q, f, f2(0.6932609677314758f, 0.6932609677314758f));
+  q = ffma2(q, f, f2(0.9999280571937561f, 0.9999280571937561f));
+  float q0, q1, t0, t1;
+  unf2(q, q0, q1);
+  unf2(t, t0, t1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
+template <int HD, bool F16, int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -141,6 +212,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr uint32_t kIdescQK = make_idesc(kFmt, kFmt, kAccF32, kQTile, kKvTile, 0, 0);
   constexpr uint32_t kIdescPV = make_idesc(kFmt, kFmt, kAccF32, kQTile, HD, 0, 1);
 
+  if (warp >= 8) {
+    reg_dealloc<80>();
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -243,8 +316,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     __syncwarp();
+  }
   } else {
     // ===================== softmax / correction / epilogue =====================
+    reg_alloc<208>();
     const int x = warp >> 2;              // Q tile of this warpgroup
     const int lane_group = warp & 3;      // TMEM lanes [32*lane_group, +32)
     const int row_in_tile = lane_group * 32 + lane;
@@ -280,31 +355,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       };
 
-      // ---- pass 1: row max (S is read from TMEM twice; a 128-register row would spill) ----
-      float mx = -INFINITY;
-      {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(tS, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 32u, rb);
-        apply_mask(ra, 0);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 64u, ra);
-        apply_mask(rb, 1);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 96u, rb);
-        apply_mask(ra, 2);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(ra[i]));
-        tmem_ld_wait();
-        apply_mask(rb, 3);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rb[i]));
-      }
+      // ---- S row -> registers (one TMEM read; the softmax warpgroups run at 216 registers) ----
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32(tS, s0);
+      tmem_ld_32x32(tS + 32u, s1);
+      tmem_ld_32x32(tS + 64u, s2);
+      tmem_ld_32x32(tS + 96u, s3);
+      tmem_ld_wait();
+      apply_mask(s0, 0);
+      apply_mask(s1, 1);
+      apply_mask(s2, 2);
+      apply_mask(s3, 3);
+      const float mx = fmaxf(fmax3(max32(s0), max32(s1), max32(s2)), max32(s3));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool need = m_new > m_run + kRescaleThreshold;  // first finite max always triggers
       if (__any_sync(0xffffffffu, need)) {
@@ -327,38 +389,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
-      // ---- pass 2: P = exp2(S*scale - m), packed 2 per column over S_X's own columns:
-      //      chunk c (S columns [32c, 32c+32)) becomes P columns [16c, 16c+16), already consumed ----
+      // ---- P = exp2(S*scale - m), packed 2 per column over the first 64 columns of S_X ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
-      float sum = 0.f;
+      const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 4 independent packed partial row sums
       auto emit = [&](uint32_t(&r)[32], int c) {
-        apply_mask(r, c);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
-          const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
-          sum += p0 + p1;
+          const uint64_t y = ffma2(f2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
+          float p0, p1;
+          if (2 * i < EMU) {
+            ex2_emulated_pair(y, p0, p1);
+          } else {
+            float y0, y1;
+            unf2(y, y0, y1);
+            p0 = ex2(y0);
+            p1 = ex2(y1);
+          }
+          acc[i & 3] = fadd2(acc[i & 3], f2(p0, p1));
           pk[i] = pack2<F16>(p0, p1);
         }
         tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
       };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
       {
-        uint32_t ra[32], rb[32];
-        tmem_ld_32x32(tS, ra);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 32u, rb);
-        emit(ra, 0);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 64u, ra);
-        emit(rb, 1);
-        tmem_ld_wait();
-        tmem_ld_32x32(tS + 96u, rb);
-        emit(ra, 2);
-        tmem_ld_wait();
-        emit(rb, 3);
+        float a0, a1, b0, b1;
+        unf2(fadd2(acc[0], acc[1]), a0, a1);
+        unf2(fadd2(acc[2], acc[3]), b0, b1);
+        l_run += (a0 + a1) + (b0 + b1);
       }
-      l_run += sum;
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready(x));
@@ -405,22 +468,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int HD, bool F16>
-static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const AttnParams& p, cudaStream_t st) {
+template <int HD, bool F16, int EMU>
+static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const AttnParams& p, cudaStream_t st) {
   using S = AttnSmem<HD>;
   static bool attr_set[64] = {};
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, F16, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   S::kTotal));
     attr_set[dev] = true;
   }
   dim3 grid((unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile)), (unsigned)p.H, (unsigned)p.B);
-  attn_fwd_kernel<HD, F16><<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  attn_fwd_kernel<HD, F16, EMU><<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
   FDM_LAUNCH_CHECK("attn_fwd kernel launch");
   return FDM_OK;
+}
+
+// how many of every 32 exponentials run on the FMA pipe instead of MUFU (tuning knob; the default is
+// the measured optimum, FDM_ATTN_EMU overrides it for experiments)
+static int attn_emu_setting(int hd) {
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("FDM_ATTN_EMU");
+    v = e ? atoi(e) : -1;
+  }
+  if (v >= 0) return v;
+  return hd == 128 ? 8 : 12;
+}
+
+template <int HD, bool F16>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                       const AttnParams& p, cudaStream_t st) {
+  const int emu = attn_emu_setting(HD);
+  if (emu <= 0) return launch_attn_e<HD, F16, 0>(tq, tk, tv, p, st);
+  if (emu <= 4) return launch_attn_e<HD, F16, 4>(tq, tk, tv, p, st);
+  if (emu <= 8) return launch_attn_e<HD, F16, 8>(tq, tk, tv, p, st);
+  if (emu <= 12) return launch_attn_e<HD, F16, 12>(tq, tk, tv, p, st);
+  return launch_attn_e<HD, F16, 16>(tq, tk, tv, p, st);
 }
 
 static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,
