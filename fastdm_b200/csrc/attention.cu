@@ -495,7 +495,7 @@ static int attn_emu_setting(int hd) {
     v = e ? atoi(e) : -1;
   }
   if (v >= 0) return v;
-  return hd == 128 ? 8 : 12;
+  return hd == 128 ? 4 : 8;
 }
 
 template <int HD, bool F16>

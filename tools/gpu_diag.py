@@ -109,14 +109,16 @@ def gemm_perf():
 def elementwise_perf():
     print("== elementwise perf (GB/s algorithmic) ==")
     res = {}
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=DEV)
+    # L2 flush by READING a 512 MB buffer: a memset would leave 126 MB of dirty lines whose write-back
+    # then competes with the kernel under test (a ~30 us artefact for kernels that move < 100 MB)
+    flush = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=DEV)
 
     def timed(fn, iters=10):
         fn()
         torch.cuda.synchronize()
         tot = 0.0
         for _ in range(iters):
-            flush.zero_()
+            flush.sum()
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
