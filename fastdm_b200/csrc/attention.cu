@@ -62,7 +62,15 @@ struct AttnParams {
   int n_kv_tiles;
   int mask_bq, mask_bk, nbq, nbk;
   float scale_log2;
+  long long* trace;  // debug: per-event clock64 stamps of CTA (0,0,0), or nullptr
 };
+
+// debug timeline: trace[(role * 8 + event) * 64 + tile] = clock64(); role 0/1 = softmax warp 0 of
+// Q tile A/B, role 2 = MMA thread. Only CTA (0,0,0) writes, only when a buffer was registered.
+constexpr int kTraceTiles = 64;
+__device__ __forceinline__ void trace_ev(const AttnParams& p, bool on, int role, int ev, uint32_t tile) {
+  if (on && tile < kTraceTiles) p.trace[(role * 8 + ev) * kTraceTiles + tile] = clock64();
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -291,8 +299,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const bool has_next = jn < p.n_kv_tiles;
           const uint32_t uV = 2 * t + 1, uKn = 2 * t + 2;
           const uint32_t ph = t & 1u;
+          const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
           wait_full(uV);
+          trace_ev(p, tr, 2, 0, t);
           mbar_wait(p_ready(0), ph);
+          trace_ev(p, tr, 2, 1, t);
           tc_fence_after();
           issue_pv(0, stage_addr(uV), t != 0);
           tc_commit(o_done(0));
@@ -301,7 +312,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             issue_qk(0, stage_addr(uKn));
             tc_commit(s_full(0));
           }
+          trace_ev(p, tr, 2, 2, t);
           mbar_wait(p_ready(1), ph);
+          trace_ev(p, tr, 2, 3, t);
           tc_fence_after();
           issue_pv(1, stage_addr(uV), t != 0);
           tc_commit(o_done(1));
@@ -335,7 +348,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t t = 0;
     for (int j = 0; j < p.n_kv_tiles; ++j) {
       if (!tile_active(j)) continue;
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+      trace_ev(p, tr, x, 0, t);
       mbar_wait(s_full(x), t & 1u);
+      trace_ev(p, tr, x, 1, t);
       tc_fence_after();
       const int valid = p.Sk - j * kKvTile;  // keys of this tile inside the sequence
       bool seg0 = true, seg1 = true;
@@ -362,6 +378,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld_32x32(tS + 64u, s2);
       tmem_ld_32x32(tS + 96u, s3);
       tmem_ld_wait();
+      trace_ev(p, tr, x, 2, t);
       apply_mask(s0, 0);
       apply_mask(s1, 1);
       apply_mask(s2, 2);
@@ -389,6 +406,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
       }
+      trace_ev(p, tr, x, 3, t);
       // ---- P = exp2(S*scale - m), packed 2 per column over the first 64 columns of S_X ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
@@ -420,11 +438,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float a0, a1, b0, b1;
         unf2(fadd2(acc[0], acc[1]), a0, a1);
         unf2(fadd2(acc[2], acc[3]), b0, b1);
-        l_run += (a0 + a1) + (b0 + b1);
+        // a row that has seen no unmasked key yet must keep l = 0: the emulated exp2 returns 2^-126, not 0,
+        // for -inf inputs (harmless next to real probabilities, but not as the only terms of the sum)
+        l_run += (m_run == -INFINITY) ? 0.f : (a0 + a1) + (b0 + b1);
       }
+      trace_ev(p, tr, x, 4, t);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_ready(x));
+      trace_ev(p, tr, x, 5, t);
       ++t;
     }
 
@@ -523,6 +545,12 @@ static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S
 
 using namespace fdm;
 
+static long long* g_attn_trace = nullptr;
+extern "C" int fdm_debug_set_attn_trace(void* device_buffer) {
+  g_attn_trace = (long long*)device_buffer;  // 3 roles x 8 events x 64 tiles x int64, or NULL to disable
+  return FDM_OK;
+}
+
 extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o,
                             const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
                             int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
@@ -571,6 +599,7 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
     p.nbk = (int)((Sk + mask_bk - 1) / mask_bk);
   }
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.trace = g_attn_trace;
   CUtensorMap tq, tk, tv;
   // batch stride of a single-batch tensor is irrelevant but must still be a legal stride
   if (B == 1) {

@@ -81,9 +81,26 @@ __device__ __forceinline__ float apply_act(float x) {
 
 struct QParams {
   float scale;  // per-row scale
+  float rcp;    // RN(1 / scale)
   float zpf;    // float(zero point) (MODE 2)
   int zp;
+  bool fast;    // x / scale may be formed as an FMA-corrected multiply (see div_by_scale)
 };
+
+// x / scale, correctly rounded. The torch oracle divides (fastdm/kernel/torch/quantize.py:35,41,66) and
+// a multiply by the reciprocal flips ~3e-4 of the codes, but a full IEEE division per
+// element (~12 instructions + a slow path) makes the kernel issue-bound well below HBM speed.
+// With r = RN(1/s): q0 = RN(x r), e = x - q0 s (exact in an FMA), q = RN(q0 + e r) is the correctly
+// rounded quotient (Markstein) as long as nothing under/overflows; rows whose scale is subnormal,
+// huge, or has an all-ones significand take the IEEE path.
+__device__ __forceinline__ float div_by_scale(float x, const QParams& p) {
+  if (p.fast) {
+    const float q0 = x * p.rcp;
+    const float e = fmaf(-q0, p.scale, x);
+    return fmaf(e, p.rcp, q0);
+  }
+  return __fdiv_rn(x, p.scale);
+}
 
 template <int MODE>
 __device__ __forceinline__ QParams make_qparams(float mn, float mx, float amax_floor) {
@@ -102,12 +119,16 @@ __device__ __forceinline__ QParams make_qparams(float mn, float mx, float amax_f
     p.zp = (int)p.zpf;
     p.zpf = (float)p.zp;
   }
+  const uint32_t sb = __float_as_uint(p.scale);
+  const uint32_t ex = (sb >> 23) & 0xffu;
+  p.fast = ex >= 16u && ex <= 238u && (sb & 0x7fffffu) != 0x7fffffu && (sb >> 31) == 0u;
+  p.rcp = p.fast ? __frcp_rn(p.scale) : 0.f;
   return p;
 }
 
 template <int MODE>
 __device__ __forceinline__ float qtransform(float x, const QParams& p) {
-  float q = __fdiv_rn(x, p.scale);
+  float q = div_by_scale(x, p);
   if (MODE == 0) {
     // torch.clamp propagates NaN (0/0 rows with a zero scale); cvt.satfinite keeps it as e4m3 NaN
     return (q != q) ? q : fminf(fmaxf(q, -448.0f), 448.0f);
@@ -115,6 +136,29 @@ __device__ __forceinline__ float qtransform(float x, const QParams& p) {
   if (MODE == 2) q = __fadd_rn(q, p.zpf);
   const float r = fminf(fmaxf(rintf(q), -128.0f), 127.0f);
   return (q != q) ? 0.0f : r;  // torch: NaN.to(int8) == 0
+}
+
+// 8 values -> 8 quantised bytes. cvt.rn.satfinite.e4m3x2 saturates to +-448 and keeps NaN;
+// cvt.rni.sat.s8.f32 rounds half-to-even, saturates to [-128,127] and maps NaN to 0 -- exactly the
+// clamp / round / cast chain of the oracle, in one instruction per value (pair).
+template <int MODE>
+__device__ __forceinline__ void quantize8(const float (&f)[8], const QParams& p, uint32_t& lo, uint32_t& hi) {
+  float q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    q[j] = div_by_scale(f[j], p);
+    if (MODE == 2) q[j] = __fadd_rn(q[j], p.zpf);
+  }
+  if (MODE == 0) {
+    lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
+    hi = cvt_e4m3x4(q[4], q[5], q[6], q[7]);
+  } else {
+    int v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(v[j]) : "f"(q[j]));
+    lo = (uint32_t)(v[0] & 0xff) | ((uint32_t)(v[1] & 0xff) << 8) | ((uint32_t)(v[2] & 0xff) << 16) | ((uint32_t)(v[3] & 0xff) << 24);
+    hi = (uint32_t)(v[4] & 0xff) | ((uint32_t)(v[5] & 0xff) << 8) | ((uint32_t)(v[6] & 0xff) << 16) | ((uint32_t)(v[7] & 0xff) << 24);
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_s8x4(float a, float b, float c, float d) {
@@ -169,18 +213,10 @@ __global__ void __launch_bounds__(512) quant_row_kernel(const T* __restrict__ in
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
-      float f[8], q[8];
+      float f[8];
       unpack8<T>(raw[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = qtransform<MODE>(f[j], p);
       uint32_t lo, hi;
-      if (MODE == 0) {
-        lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
-        hi = cvt_e4m3x4(q[4], q[5], q[6], q[7]);
-      } else {
-        lo = pack_s8x4(q[0], q[1], q[2], q[3]);
-        hi = pack_s8x4(q[4], q[5], q[6], q[7]);
-      }
+      quantize8<MODE>(f, p, lo, hi);
       stg64(dst + (int64_t)v * 8, lo, hi);
     }
   }
@@ -626,9 +662,11 @@ __global__ void __launch_bounds__(256) qk_norm_rope_head_kernel(
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, li = lane % LANES;
   const int heads = q_heads + k_heads;
-  const int64_t rows = tokens * heads;
-  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t warp_count = (int64_t)gridDim.x * (blockDim.x >> 5);
+  // 32-bit index math (the host checks tokens * heads < 2^31): a 64-bit divide per row made this
+  // kernel instruction-bound at a quarter of HBM speed
+  const int rows = (int)tokens * heads;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int warp_count = gridDim.x * (blockDim.x >> 5);
   float wqv[8], wkv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) wqv[j] = wkv[j] = 1.f;
@@ -637,19 +675,19 @@ __global__ void __launch_bounds__(256) qk_norm_rope_head_kernel(
   const float inv_cols = 1.0f / (float)head_size;
   const int half = head_size >> 1;
   constexpr int UNROLL = 4;
-  for (int64_t base = warp_global * RPW; base < rows; base += warp_count * RPW * UNROLL) {
+  for (int base = warp_global * RPW; base < rows; base += warp_count * RPW * UNROLL) {
     U128 raw[UNROLL];
     T* ptr[UNROLL];
-    int64_t tok[UNROLL];
+    int tok[UNROLL];
     bool isk[UNROLL], ok[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int64_t r = base + (int64_t)u * warp_count * RPW + sub;
+      const int r = base + u * warp_count * RPW + sub;
       ok[u] = r < rows;
       tok[u] = r / heads;
-      const int hh = (int)(r - tok[u] * heads);
+      const int hh = r - tok[u] * heads;
       isk[u] = hh >= q_heads;
-      ptr[u] = buf + tok[u] * token_stride +
+      ptr[u] = buf + (int64_t)tok[u] * token_stride +
                (isk[u] ? k_offset + (int64_t)(hh - q_heads) * head_size : q_offset + (int64_t)hh * head_size) +
                li * 8;
       raw[u] = ok[u] ? ldg128(ptr[u]) : U128{0, 0, 0, 0};
@@ -739,112 +777,140 @@ template <typename T, int MODE /*0 fp8, 2 int8 asym, 3 none*/, bool ROUND_STEPS,
 __global__ void __launch_bounds__(512) ln_mod_quant_kernel(
     const T* __restrict__ in, const float* __restrict__ A, const float* __restrict__ C,
     uint8_t* __restrict__ out, float* __restrict__ scale, int32_t* __restrict__ azp,
-    T* __restrict__ y_out, int cols, int64_t in_row_stride, int64_t y_row_stride,
-    int64_t rows_per_batch, float eps) {
+    T* __restrict__ y_out, int64_t rows, int cols, int64_t in_row_stride, int64_t y_row_stride,
+    int64_t rows_per_batch, int rows_per_cta, float eps) {
+  // grid = (row groups of one batch, batches): all rows of a CTA share the batch's mul/add vectors,
+  // which stay in registers (for rows of <= 4 vectors per thread) while the CTA walks its rows with
+  // the next row's loads already in flight.
+  constexpr bool kCacheAC = VPT <= 4;
   __shared__ float red[64];
-  const int64_t row = blockIdx.x;
   const int nvec = cols >> 3;
-  const T* src = in + row * in_row_stride;
-  const int64_t bidx = row / rows_per_batch;
+  const int64_t bidx = blockIdx.y;
+  const int64_t r_begin = bidx * rows_per_batch + (int64_t)blockIdx.x * rows_per_cta;
+  int64_t r_end = r_begin + rows_per_cta;
+  if (r_end > (bidx + 1) * rows_per_batch) r_end = (bidx + 1) * rows_per_batch;
+  if (r_end > rows) r_end = rows;
+  if (r_begin >= r_end) return;
   const float* Ar = A ? A + bidx * cols : nullptr;
   const float* Cr = C ? C + bidx * cols : nullptr;
-  U128 raw[VPT];
-  float sum = 0.f;
+  auto load_ac = [&](const float* base, int v, float fill, float (&dst)[8]) {
+    if (base) {
+      const float4 x0 = *reinterpret_cast<const float4*>(base + v * 8);
+      const float4 x1 = *reinterpret_cast<const float4*>(base + v * 8 + 4);
+      dst[0] = x0.x; dst[1] = x0.y; dst[2] = x0.z; dst[3] = x0.w;
+      dst[4] = x1.x; dst[5] = x1.y; dst[6] = x1.z; dst[7] = x1.w;
+    } else {
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int v = threadIdx.x + i * blockDim.x;
-    if (v < nvec) {
-      raw[i] = ldg128_stream(src + (int64_t)v * 8);
-      float f[8];
-      unpack8<T>(raw[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += f[j];
+      for (int j = 0; j < 8; ++j) dst[j] = fill;
     }
-  }
-  const float mean = block_sum(sum, red) / (float)cols;
-  float sq = 0.f;
+  };
+  float ac[kCacheAC ? VPT : 1][8], cc[kCacheAC ? VPT : 1][8];
+  if (kCacheAC) {
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int v = threadIdx.x + i * blockDim.x;
-    if (v < nvec) {
-      float f[8];
-      unpack8<T>(raw[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d = f[j] - mean;
-        sq += d * d;
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        load_ac(Ar, v, 1.f, ac[kCacheAC ? i : 0]);
+        load_ac(Cr, v, 0.f, cc[kCacheAC ? i : 0]);
       }
     }
   }
-  const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
-  float mn = INFINITY, mx = -INFINITY;
+  U128 raw[VPT], nxt[VPT];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
-    if (v < nvec) {
-      float f[8];
-      unpack8<T>(raw[i], f);
-      float a[8], c[8];
+    if (v < nvec) raw[i] = ldg128_stream(in + r_begin * in_row_stride + (int64_t)v * 8);
+  }
+  for (int64_t row = r_begin; row < r_end; ++row) {
+    if (row + 1 < r_end) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] = 1.f;
-        c[j] = 0.f;
+      for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * blockDim.x;
+        if (v < nvec) nxt[i] = ldg128_stream(in + (row + 1) * in_row_stride + (int64_t)v * 8);
       }
-      if (Ar) {
-        const float4 a0 = *reinterpret_cast<const float4*>(Ar + v * 8);
-        const float4 a1 = *reinterpret_cast<const float4*>(Ar + v * 8 + 4);
-        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-      }
-      if (Cr) {
-        const float4 c0 = *reinterpret_cast<const float4*>(Cr + v * 8);
-        const float4 c1 = *reinterpret_cast<const float4*>(Cr + v * 8 + 4);
-        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
-      }
+    }
+    float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float n = (f[j] - mean) * rstd;
-        if (ROUND_STEPS) {
-          n = round_to<T>(n);
-          if (Ar) n = round_to<T>(__fmul_rn(n, a[j]));
-          if (Cr) n = __fadd_rn(n, c[j]);
-        } else {
-          if (Ar) n = __fmul_rn(n, a[j]);
-          if (Cr) n = __fadd_rn(n, c[j]);
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        float f[8];
+        unpack8<T>(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += f[j];
+      }
+    }
+    const float mean = block_sum(sum, red) / (float)cols;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        float f[8];
+        unpack8<T>(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[j] - mean;
+          sq += d * d;
         }
-        f[j] = round_to<T>(n);
-        mn = fminf(mn, f[j]);
-        mx = fmaxf(mx, f[j]);
       }
-      raw[i] = pack8<T>(f);
-      if (y_out) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
     }
-  }
-  if (MODE == 3) return;
-  MinMax r = block_minmax(mn, mx, red);
-  const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(r.mn, r.mx, fp8_amax_floor<T>());
-  if (threadIdx.x == 0) {
-    scale[row] = p.scale;
-    if (MODE == 2) azp[row] = p.zp;
-  }
-  uint8_t* dst = out + row * (int64_t)cols;
+    const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
+    float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int v = threadIdx.x + i * blockDim.x;
-    if (v < nvec) {
-      float f[8], q[8];
-      unpack8<T>(raw[i], f);
+    for (int i = 0; i < VPT; ++i) {
+      const int v = threadIdx.x + i * blockDim.x;
+      if (v < nvec) {
+        float f[8];
+        unpack8<T>(raw[i], f);
+        float al[8], cl[8];
+        if (!kCacheAC) {
+          load_ac(Ar, v, 1.f, al);
+          load_ac(Cr, v, 0.f, cl);
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) q[j] = qtransform<MODE == 3 ? 0 : MODE>(f[j], p);
-      uint32_t lo, hi;
-      if (MODE == 0) {
-        lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
-        hi = cvt_e4m3x4(q[4], q[5], q[6], q[7]);
-      } else {
-        lo = pack_s8x4(q[0], q[1], q[2], q[3]);
-        hi = pack_s8x4(q[4], q[5], q[6], q[7]);
+        for (int j = 0; j < 8; ++j) {
+          const float a = kCacheAC ? ac[kCacheAC ? i : 0][j] : al[j];
+          const float c = kCacheAC ? cc[kCacheAC ? i : 0][j] : cl[j];
+          float n = (f[j] - mean) * rstd;
+          if (ROUND_STEPS) {
+            n = round_to<T>(n);
+            if (Ar) n = round_to<T>(__fmul_rn(n, a));
+            if (Cr) n = __fadd_rn(n, c);
+          } else {
+            if (Ar) n = __fmul_rn(n, a);
+            if (Cr) n = __fadd_rn(n, c);
+          }
+          f[j] = round_to<T>(n);
+          mn = fminf(mn, f[j]);
+          mx = fmaxf(mx, f[j]);
+        }
+        raw[i] = pack8<T>(f);
+        if (y_out) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
       }
-      stg64(dst + (int64_t)v * 8, lo, hi);
     }
+    if (MODE != 3) {
+      MinMax r = block_minmax(mn, mx, red);
+      const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(r.mn, r.mx, fp8_amax_floor<T>());
+      if (threadIdx.x == 0) {
+        scale[row] = p.scale;
+        if (MODE == 2) azp[row] = p.zp;
+      }
+      uint8_t* dst = out + row * (int64_t)cols;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int v = threadIdx.x + i * blockDim.x;
+        if (v < nvec) {
+          float f[8];
+          unpack8<T>(raw[i], f);
+          uint32_t lo, hi;
+          quantize8<MODE == 3 ? 0 : MODE>(f, p, lo, hi);
+          stg64(dst + (int64_t)v * 8, lo, hi);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) raw[i] = nxt[i];
   }
 }
 
@@ -1050,6 +1116,7 @@ int fdm_qk_norm_rope(void* buf, const void* wq, const void* wk, const void* cos_
     const int lanes = head_size / 8;
     const int rpw = 32 / lanes;
     const int64_t rows = tokens * (q_heads + k_heads);
+    FDM_REQUIRE(rows < (1LL << 31) - (1LL << 24), "qk_norm_rope: tokens * heads must stay below 2^31");
     int64_t want = ((rows + rpw - 1) / rpw + 8 * 4 - 1) / (8 * 4);
     const int64_t cap = (int64_t)num_sms() * 32;
     if (want > cap) want = cap;
@@ -1102,10 +1169,14 @@ static void launch_lnq(const void* in, const float* A, const float* C, void* out
   int block = (((nvec + 3) / 4 + 31) / 32) * 32;
   if (block > 512) block = 512;
   const int vpt = (nvec + block - 1) / block;
-  const unsigned g = (unsigned)rows;
+  // rows per CTA: enough CTAs for ~8 per SM, at most 8 rows each
+  const int64_t batches = (rows + rpb - 1) / rpb;
+  int rpc = 8;
+  while (rpc > 1 && batches * ((rpb + rpc - 1) / rpc) < (int64_t)num_sms() * 8) rpc >>= 1;
+  dim3 g((unsigned)((rpb + rpc - 1) / rpc), (unsigned)batches);
 #define LNQ(V)                                                                                      \
   ln_mod_quant_kernel<T, MODE, RS, V><<<g, block, 0, st>>>((const T*)in, A, C, (uint8_t*)out, scale, \
-                                                           azp, (T*)y, cols, is, ys, rpb, eps)
+                                                           azp, (T*)y, rows, cols, is, ys, rpb, rpc, eps)
   if (vpt <= 1) LNQ(1);
   else if (vpt <= 2) LNQ(2);
   else if (vpt <= 4) LNQ(4);
@@ -1133,7 +1204,8 @@ int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* 
               "layernorm_modulate_quant: mul/add must be 16-byte aligned fp32");
   FDM_REQUIRE(y_out == nullptr || (y_row_stride % 8 == 0 && (uintptr_t)y_out % 16 == 0),
               "layernorm_modulate_quant: y_out alignment");
-  FDM_REQUIRE(rows < (1LL << 31), "layernorm_modulate_quant: too many rows");
+  FDM_REQUIRE(rows < (1LL << 31) && (rows + rows_per_batch - 1) / rows_per_batch < 65536,
+              "layernorm_modulate_quant: too many rows / batches");
   const bool q8 = out_dtype == FDM_E4M3, s8 = out_dtype == FDM_S8;
   if (q8 || s8) {
     FDM_REQUIRE(out && scale && (!s8 || azp), "layernorm_modulate_quant: null output");

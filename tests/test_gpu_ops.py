@@ -193,12 +193,18 @@ def test_rope_flux_shape_and_strided_views(ops):
 
 # ------------------------------------------------------------------ gelu_and_mul
 def gelu_close(y, want):
-    """GPU erff vs torch's CPU erf differ in the last fp32 bits; for very negative gates the GELU is a
-    cancellation (1 + erf(x) ~ 1e-7) so *relative* differences of tiny outputs are meaningless.
-    Bar: the reference test's tolerance (tests/test_gelu_and_mul.py:20 -> bf16 assert_close defaults,
-    rtol 1.6e-2 / atol 1e-5) and at most 1% of the elements differing at all."""
-    torch.testing.assert_close(y.cpu(), want.cpu(), rtol=1.6e-2, atol=1e-5)
-    assert float((y.cpu() != want.cpu()).float().mean()) < 1e-2
+    """The kernels evaluate GELU with ex2/rcp-based formulas (abs. error ~1.5e-7 on Phi(x)); torch uses
+    libm erf/tanh. For very negative gates the GELU is a cancellation (Phi(x) ~ 1e-5) so *relative*
+    differences of those tiny outputs are meaningless in either implementation.
+    Bar: the reference test's tolerance everywhere (tests/test_gelu_and_mul.py:20 -> bf16 assert_close
+    defaults, rtol 1.6e-2 / atol 1e-5), and among the outputs of meaningful magnitude
+    (|y| > 2^-10 of the tensor's max) at most 1% differ at all, by at most 1 bf16 ulp."""
+    y, want = y.cpu(), want.cpu()
+    torch.testing.assert_close(y, want, rtol=1.6e-2, atol=1e-5)
+    big = want.float().abs() > want.float().abs().max() * 2.0 ** -10
+    assert float((y[big] != want[big]).float().mean()) < 1e-2
+    d = (y[big].view(torch.int16).int() - want[big].view(torch.int16).int()).abs()
+    assert int(d.max()) <= 1
 
 
 def test_gelu_and_mul(ops):
@@ -220,8 +226,11 @@ def test_gelu_quant_fusion_matches_unfused(ops):
         act = torch.nn.functional.gelu(xd, approximate=approx)  # what the reference layers compute unfused
         q, s = ops.gelu_quantize_to_fp8(xd, approximate=approx)
         rq, rs = ops.quantize_to_fp8(act)
-        # GPU libm vs torch's GELU differ by 1 bf16 ulp on rare elements; the codes then differ rarely
-        assert float((q.view(torch.uint8) != rq.view(torch.uint8)).float().mean()) < 2e-3
+        # our GELU vs torch's differ by 1 bf16 ulp on ~1% of the elements (mostly tiny ones); the fp8 codes
+        # (3 mantissa bits) then differ far more rarely, and never by more than one code step
+        qa, qb = q.view(torch.uint8).int(), rq.view(torch.uint8).int()
+        assert float((qa != qb).float().mean()) < 1e-2
+        assert int((qa - qb).abs().max()) <= 1
         assert torch.allclose(s, rs, rtol=1e-2)
 
 
