@@ -41,11 +41,11 @@ constexpr int kKvTile = 128;  // keys per KV tile (UMMA N of QK^T, K extent of P
 constexpr int kMaxKvTiles = 8192;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
-template <int HD>
+template <int HD, int ES>
 struct AttnSmem {
-  static constexpr int kHalves = HD / 64;              // 64-element (128 B) column groups per row
-  static constexpr int kTileBytes = kKvTile * HD * 2;  // one Q / K / V tile
-  static constexpr int kStages = HD == 128 ? 4 : 6;
+  static constexpr int kHalves = HD * ES / 128;         // 128-byte column groups per row
+  static constexpr int kTileBytes = kKvTile * HD * ES;  // one Q / K / V tile
+  static constexpr int kStages = kTileBytes == 32768 ? 4 : 6;
   static constexpr int kQOff = 0;
   static constexpr int kKvOff = 2 * kTileBytes;
   static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
@@ -78,9 +78,11 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-template <bool F16>
+// operand dtype of q/k/v (and of P): 0 = bf16, 1 = fp16, 2 = fp8 e4m3
+constexpr int kDtBF16 = 0, kDtF16 = 1, kDtE4M3 = 2;
+template <int DT>
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  return F16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
+  return DT == kDtF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
 }
 
 // per-warpgroup register re-budgeting (the kernel is launched at 168 regs/thread = 65536 / 384)
@@ -152,11 +154,13 @@ __device__ __forceinline__ void ex2_emulated_pair(uint64_t y, float& p0, float& 
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-template <int HD, bool F16, int EMU>
+template <int HD, int DT, int EMU>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
-  using S = AttnSmem<HD>;
+  constexpr int ES = DT == kDtE4M3 ? 1 : 2;  // operand element size
+  constexpr bool F16 = DT == kDtF16;
+  using S = AttnSmem<HD, ES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -216,9 +220,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
   auto tile_active = [&](int j) -> bool { return !has_mask || flags[j] != 0; };
 
-  constexpr uint32_t kFmt = F16 ? kFmtF16 : kFmtBF16;
+  constexpr uint32_t kFmt = DT == kDtE4M3 ? kFmtE4M3 : (F16 ? kFmtF16 : kFmtBF16);
+  constexpr MmaKind kKind = DT == kDtE4M3 ? MmaKind::F8F6F4 : MmaKind::F16;
   constexpr uint32_t kIdescQK = make_idesc(kFmt, kFmt, kAccF32, kQTile, kKvTile, 0, 0);
   constexpr uint32_t kIdescPV = make_idesc(kFmt, kFmt, kAccF32, kQTile, HD, 0, 1);
+  constexpr int kBoxElems = 128 / ES;   // elements per 128-byte swizzled row
+  constexpr int kKeysPerPV = 32 / ES;   // keys per P.V tcgen05.mma (K = 32 bytes of operand)
 
   if (warp >= 8) {
     reg_dealloc<80>();
@@ -231,7 +238,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int hf = 0; hf < S::kHalves; ++hf)
           tma_load_4d(base + S::kQOff + x * S::kTileBytes + hf * (kQTile * 128), &tmap_q, q_full,
-                      hf * 64, h, q0 + x * kQTile, b);
+                      hf * kBoxElems, h, q0 + x * kQTile, b);
       uint32_t u = 0;
       for (int j = 0; j < p.n_kv_tiles; ++j) {
         if (!tile_active(j)) continue;
@@ -245,7 +252,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int hf = 0; hf < S::kHalves; ++hf)
             tma_load_4d(dst + hf * (kKvTile * 128), kv == 0 ? &tmap_k : &tmap_v, kv_full(stage),
-                        hf * 64, h, j * kKvTile, b);
+                        hf * kBoxElems, h, j * kKvTile, b);
           ++u;
         }
       }
@@ -259,19 +266,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t q_smem[2] = {base + S::kQOff, base + S::kQOff + S::kTileBytes};
       auto issue_qk = [&](int x, uint32_t k_smem) {
 #pragma unroll
-        for (int ks = 0; ks < HD / 16; ++ks) {
+        for (int ks = 0; ks < HD * ES / 32; ++ks) {  // 32 bytes of head dim per MMA
           const uint32_t off = (uint32_t)(ks / 4) * (kQTile * 128) + (uint32_t)(ks % 4) * 32u;
-          umma_ss<MmaKind::F16, 1>(tS[x], make_desc_kmajor_sw128(q_smem[x] + off),
-                                   make_desc_kmajor_sw128(k_smem + off), kIdescQK, ks != 0);
+          umma_ss<kKind, 1>(tS[x], make_desc_kmajor_sw128(q_smem[x] + off),
+                            make_desc_kmajor_sw128(k_smem + off), kIdescQK, ks != 0);
         }
       };
       auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate) {
 #pragma unroll
-        for (int ks = 0; ks < kKvTile / 16; ++ks) {
-          // 16 keys = 16 rows of 128 B; P: 16 bf16 = 8 TMEM columns
-          const uint64_t bdesc = make_desc_mnmajor_sw128(v_smem + (uint32_t)ks * 2048u, kKvTile * 128, 1024);
-          umma_ts<MmaKind::F16>(tO[x], tS[x] + (uint32_t)ks * 8u, bdesc, kIdescPV,
-                                (accumulate || ks != 0) ? 1u : 0u);
+        for (int ks = 0; ks < kKvTile / kKeysPerPV; ++ks) {
+          // kKeysPerPV keys = that many 128-byte rows of V; the matching slice of P is 8 TMEM columns
+          const uint64_t bdesc = make_desc_mnmajor_sw128(v_smem + (uint32_t)(ks * kKeysPerPV * 128),
+                                                         kKvTile * 128, 1024);
+          umma_ts<kKind>(tO[x], tS[x] + (uint32_t)ks * 8u, bdesc, kIdescPV,
+                         (accumulate || ks != 0) ? 1u : 0u);
         }
       };
       auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kTileBytes; };
@@ -413,6 +421,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 4 independent packed partial row sums
       auto emit = [&](uint32_t(&r)[32], int c) {
         uint32_t pk[16];
+        float pv[32];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint64_t y = ffma2(f2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
@@ -426,9 +435,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             p1 = ex2(y1);
           }
           acc[i & 3] = fadd2(acc[i & 3], f2(p0, p1));
-          pk[i] = pack2<F16>(p0, p1);
+          if (DT == kDtE4M3) {
+            pv[2 * i] = p0;
+            pv[2 * i + 1] = p1;
+          } else {
+            pk[i] = pack2<DT>(p0, p1);
+          }
         }
-        tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
+        if (DT == kDtE4M3) {
+          // P -> e4m3, unscaled (the reference's fp8 semantics), 4 keys per TMEM column
+          uint32_t p8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) p8[i] = cvt_e4m3x4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+          tmem_st_32x8(tS + (uint32_t)(c * 8), p8);
+        } else {
+          tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
+        }
       };
       emit(s0, 0);
       emit(s1, 1);
@@ -472,10 +494,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           U128 o;
-          o.x = pack2<F16>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
-          o.y = pack2<F16>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
-          o.z = pack2<F16>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
-          o.w = pack2<F16>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
+          o.x = pack2<DT>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
+          o.y = pack2<DT>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
+          o.z = pack2<DT>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
+          o.w = pack2<DT>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
           stg128(out_row + c * 32 + q * 8, o);
         }
       }
@@ -490,20 +512,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int HD, bool F16, int EMU>
+template <int HD, int DT, int EMU>
 static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const AttnParams& p, cudaStream_t st) {
-  using S = AttnSmem<HD>;
+  using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2>;
   static bool attr_set[64] = {};
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, F16, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DT, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   S::kTotal));
     attr_set[dev] = true;
   }
   dim3 grid((unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile)), (unsigned)p.H, (unsigned)p.B);
-  attn_fwd_kernel<HD, F16, EMU><<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
+  attn_fwd_kernel<HD, DT, EMU><<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
   FDM_LAUNCH_CHECK("attn_fwd kernel launch");
   return FDM_OK;
 }
@@ -520,25 +542,25 @@ static int attn_emu_setting(int hd) {
   return hd == 128 ? 4 : 8;
 }
 
-template <int HD, bool F16>
+template <int HD, int DT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, cudaStream_t st) {
   const int emu = attn_emu_setting(HD);
-  if (emu <= 0) return launch_attn_e<HD, F16, 0>(tq, tk, tv, p, st);
-  if (emu <= 4) return launch_attn_e<HD, F16, 4>(tq, tk, tv, p, st);
-  if (emu <= 8) return launch_attn_e<HD, F16, 8>(tq, tk, tv, p, st);
-  if (emu <= 12) return launch_attn_e<HD, F16, 12>(tq, tk, tv, p, st);
-  return launch_attn_e<HD, F16, 16>(tq, tk, tv, p, st);
+  if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st);
+  if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st);
+  if (emu <= 8) return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st);
+  if (emu <= 12) return launch_attn_e<HD, DT, 12>(tq, tk, tv, p, st);
+  return launch_attn_e<HD, DT, 16>(tq, tk, tv, p, st);
 }
 
 static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,
-                         int64_t batch_stride, int64_t token_stride) {
-  // dims innermost first: d, head, token, batch
+                         int64_t batch_stride, int64_t token_stride, int es) {
+  // dims innermost first: d, head, token, batch; one box = 128 rows x 128 bytes
   uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)S, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)hd * 2, (uint64_t)token_stride * 2, (uint64_t)batch_stride * 2};
-  uint32_t box[4] = {64, 1, 128, 1};
-  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, ptr, dims, strides, box,
-                   CU_TENSOR_MAP_SWIZZLE_128B);
+  uint64_t strides[3] = {(uint64_t)hd * es, (uint64_t)token_stride * es, (uint64_t)batch_stride * es};
+  uint32_t box[4] = {(uint32_t)(128 / es), 1, 128, 1};
+  return make_tmap(out, es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, ptr,
+                   dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace fdm
@@ -562,17 +584,20 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   if (B == 0 || Sq == 0) return FDM_OK;
   FDM_REQUIRE(q && k && v && o, "attn: null pointer");
   FDM_REQUIRE(hd == 64 || hd == 128, "attn: head_dim %d unsupported (64 or 128)", hd);
-  if (qkv_dtype == FDM_E4M3) {
-    set_error("attn: fp8 q/k/v is not built in this version");
+  FDM_REQUIRE(qkv_dtype == FDM_BF16 || qkv_dtype == FDM_F16 || qkv_dtype == FDM_E4M3,
+              "attn: q/k/v dtype must be bf16, f16 or e4m3");
+  const int es = qkv_dtype == FDM_E4M3 ? 1 : 2;
+  if (es == 1 && hd != 128) {
+    set_error("attn: fp8 q/k/v is built for head_dim 128 only");
     return FDM_ERR_UNSUPPORTED;
   }
-  FDM_REQUIRE(qkv_dtype == FDM_BF16 || qkv_dtype == FDM_F16, "attn: q/k/v dtype must be bf16 or f16");
   FDM_REQUIRE(scale > 0.f, "attn: scale must be positive");
   FDM_REQUIRE(Sk > 0, "attn: empty key sequence");
   FDM_REQUIRE(Sq < (1LL << 31) && Sk <= (int64_t)kMaxKvTiles * kKvTile && H < 65536 && B < 65536,
               "attn: sequence too long (Sk <= %d)", kMaxKvTiles * kKvTile);
-  for (int64_t s : {q_ts, k_ts, v_ts, q_bs, k_bs, v_bs, o_ts, o_bs})
-    FDM_REQUIRE(s % 8 == 0, "attn: strides must be multiples of 8 elements (16 bytes)");
+  for (int64_t s : {q_ts, k_ts, v_ts, q_bs, k_bs, v_bs})
+    FDM_REQUIRE((s * es) % 16 == 0, "attn: q/k/v strides must be multiples of 16 bytes");
+  FDM_REQUIRE(o_ts % 8 == 0 && o_bs % 8 == 0, "attn: output strides must be multiples of 8 elements");
   FDM_REQUIRE((uintptr_t)q % 16 == 0 && (uintptr_t)k % 16 == 0 && (uintptr_t)v % 16 == 0 &&
                   (uintptr_t)o % 16 == 0,
               "attn: pointers must be 16-byte aligned");
@@ -607,14 +632,15 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
     k_bs = Sk * k_ts;
     v_bs = Sk * v_ts;
   }
-  rc = make_qkv_tmap(&tq, q, B, Sq, H, hd, q_bs, q_ts);
+  rc = make_qkv_tmap(&tq, q, B, Sq, H, hd, q_bs, q_ts, es);
   if (rc) return rc;
-  rc = make_qkv_tmap(&tk, k, B, Sk, H, hd, k_bs, k_ts);
+  rc = make_qkv_tmap(&tk, k, B, Sk, H, hd, k_bs, k_ts, es);
   if (rc) return rc;
-  rc = make_qkv_tmap(&tv, v, B, Sk, H, hd, v_bs, v_ts);
+  rc = make_qkv_tmap(&tv, v, B, Sk, H, hd, v_bs, v_ts, es);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
+  if (qkv_dtype == FDM_E4M3) return launch_attn<128, kDtE4M3>(tq, tk, tv, p, st);
   const bool f16 = qkv_dtype == FDM_F16;
-  if (hd == 128) return f16 ? launch_attn<128, true>(tq, tk, tv, p, st) : launch_attn<128, false>(tq, tk, tv, p, st);
-  return f16 ? launch_attn<64, true>(tq, tk, tv, p, st) : launch_attn<64, false>(tq, tk, tv, p, st);
+  if (hd == 128) return f16 ? launch_attn<128, kDtF16>(tq, tk, tv, p, st) : launch_attn<128, kDtBF16>(tq, tk, tv, p, st);
+  return f16 ? launch_attn<64, kDtF16>(tq, tk, tv, p, st) : launch_attn<64, kDtBF16>(tq, tk, tv, p, st);
 }

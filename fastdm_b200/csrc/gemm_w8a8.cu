@@ -7,7 +7,8 @@
 //   warp 1   : MMA issuer    -- one elected thread issues tcgen05.mma (kind::f8f6f4 / kind::i8),
 //              accumulators live in TMEM (2 x BN columns, double buffered across tiles);
 //              tcgen05.commit releases smem stages and publishes finished accumulators
-//   warps 2-5: epilogue      -- tcgen05.ld the 128 x BN accumulator (one row per thread), apply
+//   warps 2-9: epilogue      -- two warps per TMEM lane quarter, each taking half of the BN columns:
+//              tcgen05.ld the 128 x BN accumulator (one row per thread), apply
 //              sA[m]*sB[n] (+azp rank-1 correction) (+bias) (+GELU), round, 16-byte global stores.
 //              Runs concurrently with the next tile's main loop.
 //
@@ -23,8 +24,8 @@ using namespace sm100;
 constexpr int kBM = 128;          // rows per tile (UMMA M, cta_group::1)
 constexpr int kBK = 128;          // bytes (= 8-bit elements) of K per stage: one 128B swizzle row
 constexpr int kUmmaK = 32;        // K per tcgen05.mma for 8-bit operands
-constexpr int kGemmThreads = 192; // 6 warps
-constexpr int kEpiThreads = 128;
+constexpr int kGemmThreads = 320; // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kGroupM = 16;       // m-tiles per rasterisation group (L2 reuse of B)
 
 template <int BN>
@@ -74,7 +75,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tn = r / gm;
 }
 
-template <bool INT8, int BN>
+template <bool INT8, int BN, int ACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -106,7 +107,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), 8);
     }
     fence_mbar_init();
   }
@@ -190,6 +191,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue warps =====================
     const int epi_tid = threadIdx.x - 64;
     const int lane_group = warp & 3;  // TMEM lanes [32*lane_group, +32) are this warp's
+    const int col_half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     const int row_in_tile = lane_group * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -220,12 +222,27 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (INT8) zp = (row_ok && p.azp != nullptr) ? p.azp[row] : 0;
       const bool has_bias = p.bias != nullptr;
 
+      // the residual rows do not depend on the accumulator: fetch this warp's share (BN/2 columns of its
+      // row, 16-byte pieces) before waiting for the main loop, so their DRAM latency hides under it
+      constexpr int kMyChunks = BN / 64;
+      U128 resv[kMyChunks][4];
+      if (p.residual != nullptr && row_ok) {
+        const uint16_t* rrow = reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)row * p.ldr + n0;
+#pragma unroll
+        for (int cc = 0; cc < kMyChunks; ++cc) {
+          const int c = col_half * kMyChunks + cc;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (n0 + c * 32 + q * 8 < p.N) resv[cc][q] = ldg128(rrow + c * 32 + q * 8);
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BN);
       const int n_valid = min(BN, p.N - n0);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+#pragma unroll
+      for (int cc = 0; cc < kMyChunks; ++cc) {
+        const int c = col_half * kMyChunks + cc;
         if (c * 32 >= n_valid) break;
         uint32_t r[32];
         tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
@@ -249,12 +266,12 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           v[j] = x;
         }
-        if (p.act != FDM_ACT_NONE) {
+        if (ACT != FDM_ACT_NONE) {
           // unfused reference: GEMM output is rounded to T, then F.gelu runs on that tensor
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = (p.out_dtype == FDM_BF16) ? round_to<__nv_bfloat16>(v[j]) : round_to<__half>(v[j]);
-            v[j] = (p.act == FDM_ACT_GELU_TANH) ? gelu_tanh(x) : gelu_erf(x);
+            v[j] = (ACT == FDM_ACT_GELU_TANH) ? gelu_tanh(x) : gelu_erf(x);
           }
         }
         if (row_ok) {
@@ -264,9 +281,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // reference chains (flux.py:153-154,161-163,69-72; wan.py:97,105,112): the linear's output
             // is a T tensor, then gate * out (+ rounding for bf16 tensor ops), then residual + .
             const float* grow = p.gate ? p.gate + (int64_t)(row / p.rows_per_batch) * p.N + col0 : nullptr;
-            const uint16_t* rrow = p.residual
-                                       ? reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)row * p.ldr + col0
-                                       : nullptr;
+            const bool has_res = p.residual != nullptr;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (col0 + q * 8 < p.N) {
@@ -282,9 +297,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   gq[0] = g0.x; gq[1] = g0.y; gq[2] = g0.z; gq[3] = g0.w;
                   gq[4] = g1.x; gq[5] = g1.y; gq[6] = g1.z; gq[7] = g1.w;
                 }
-                if (rrow) {
-                  const U128 rv = ldg128(rrow + q * 8);
-                  if (bf) unpack8<__nv_bfloat16>(rv, rq); else unpack8<__half>(rv, rq);
+                if (has_res) {
+                  if (bf) unpack8<__nv_bfloat16>(resv[cc][q], rq); else unpack8<__half>(resv[cc][q], rq);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -349,23 +363,31 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <bool INT8, int BN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                       cudaStream_t st) {
+template <bool INT8, int BN, int ACT>
+static int launch_gemm_a(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                         cudaStream_t st) {
   using S = GemmSmem<BN>;
   static bool attr_set[64] = {};
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev]) {
-    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN>,
+    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN, ACT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set[dev] = true;
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_w8a8_kernel<INT8, BN><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  gemm_w8a8_kernel<INT8, BN, ACT><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, p);
   FDM_LAUNCH_CHECK("gemm_w8a8 kernel launch");
   return FDM_OK;
+}
+
+template <bool INT8, int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                       cudaStream_t st) {
+  if (p.act == FDM_ACT_GELU_TANH) return launch_gemm_a<INT8, BN, FDM_ACT_GELU_TANH>(ta, tb, p, st);
+  if (p.act == FDM_ACT_GELU_ERF) return launch_gemm_a<INT8, BN, FDM_ACT_GELU_ERF>(ta, tb, p, st);
+  return launch_gemm_a<INT8, BN, FDM_ACT_NONE>(ta, tb, p, st);
 }
 
 static int gemm_common(bool int8, const void* a, const void* b, const float* scale_a,

@@ -193,7 +193,8 @@ int fdm_gemm_int8_residual(const void* a, const void* b, const float* scale_a, c
  *     column slice of a wider buffer (FLUX single block: cat([attn, mlp]) without the cat);
  *     always BF16 (F16 when qkv_dtype is F16)
  *   qkv_dtype: FDM_BF16 | FDM_F16 | FDM_E4M3 (fp8: per-tensor descale 1.0, P quantised to e4m3
- *              unscaled -- the reference's only fp8 semantics, csrc/attention/interface.cu:262-270)
+ *              unscaled -- the reference's only fp8 semantics, csrc/attention/interface.cu:262-270;
+ *              head_dim 128 only, output bf16)
  *   hd in {64, 128}
  *   block_mask: NULL (dense) or int8 [B, H, ceil(Sq/mask_bq), ceil(Sk/mask_bk)], 1 = compute,
  *               0 = skip (excluded from the softmax); mask_bq in {64,128}, mask_bk in {64,128}

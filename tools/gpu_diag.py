@@ -224,6 +224,67 @@ def attn_patterns():
                 print("   periodic-onehot err:", (y1.float() - r1).abs().max().item())
 
 
+def block_kernels_perf():
+    """Fused block kernels + GELU-epilogue GEMMs, timed as back-to-back launches rotating over enough
+    buffers to exceed the 126 MB L2 (no host gaps, no flush artefacts)."""
+    print("== fused block kernels ==")
+    res = {}
+
+    def rot_time(make, run, nbuf, iters=40):
+        bufs = [make() for _ in range(nbuf)]
+        for b in bufs:
+            run(b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            run(bufs[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    for (M, K) in ((8704, 3072), (8704, 15360), (80640, 5120)):
+        nbuf = max(2, int(400e6 // (M * K * 2)) + 1)
+        a = torch.rand(1, K, device=DEV) + 0.5
+        c = torch.rand(1, K, device=DEV)
+        ms = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF),
+                      lambda x: ops.layernorm_modulate_quant(x, a, c, M, torch.float8_e4m3fn), nbuf)
+        gb = (3 * M * K + 4 * M) / ms / 1e6
+        ms2 = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF), lambda x: ops.quantize_to_fp8(x), nbuf)
+        gb2 = (3 * M * K + 4 * M) / ms2 / 1e6
+        print(f"[{M},{K}] ln_mod_quant {ms*1e3:.1f} us {gb:.0f} GB/s | quant_fp8 {ms2*1e3:.1f} us {gb2:.0f} GB/s")
+        res[f"lnq_{M}x{K}"] = dict(lnq_us=ms * 1e3, lnq_gbs=gb, quant_us=ms2 * 1e3, quant_gbs=gb2)
+    for (S, H, across) in ((8704, 24, False), (80640, 40, True)):
+        d = H * 128
+        nbuf = max(2, int(400e6 // (S * 3 * d * 2)) + 1)
+        wq = torch.randn(d if across else 128, device=DEV, dtype=BF)
+        cs = torch.rand(S, 128, device=DEV, dtype=BF)
+        ms = rot_time(lambda: torch.randn(S, 3 * d, device=DEV, dtype=BF),
+                      lambda x: ops.qk_norm_rope_(x, wq, wq, cs, H, H, 128, 0, d, 0, 1e-6, across), nbuf, iters=20)
+        gb = 8 * S * d / ms / 1e6
+        print(f"qk_norm_rope S{S} H{H} across={across}: {ms*1e3:.1f} us {gb:.0f} GB/s")
+        res[f"qknr_{S}x{H}"] = dict(us=ms * 1e3, gbs=gb)
+    for (M, K, N) in ((8704, 3072, 12288), (8704, 15360, 3072), (8192, 3072, 3072)):
+        g = torch.Generator(device=DEV).manual_seed(1)
+        a = torch.randn(M, K, device=DEV, generator=g).to(torch.float8_e4m3fn)
+        b = (torch.randn(N, K, device=DEV, generator=g) * 0.05).to(torch.float8_e4m3fn).t()
+        sa = torch.rand(M, 1, device=DEV) * 0.1
+        sb = torch.rand(N, 1, device=DEV)
+        bias = torch.randn(N, device=DEV).to(BF)
+        resid = torch.randn(M, N, device=DEV).to(BF)
+        gate = torch.randn(1, N, device=DEV)
+        obuf = torch.empty(M, N, device=DEV, dtype=BF)
+        fl = 2.0 * M * N * K
+        t_plain = timeit(lambda: ops.fp8_matmul(a, b, sa, sb, BF, bias, out=obuf))
+        t_tanh = timeit(lambda: ops.fp8_matmul(a, b, sa, sb, BF, bias, act="gelu_tanh", out=obuf))
+        t_erf = timeit(lambda: ops.fp8_matmul(a, b, sa, sb, BF, bias, act="gelu_erf", out=obuf))
+        t_res = timeit(lambda: ops.fp8_matmul(a, b, sa, sb, BF, bias, gate=gate, residual=resid, rows_per_batch=M, out=obuf))
+        print(f"gemm M{M} K{K} N{N}: plain {t_plain*1e3:.0f} us {fl/t_plain/1e9:.0f} TF | gelu_tanh {t_tanh*1e3:.0f} us {fl/t_tanh/1e9:.0f} TF"
+              f" | gelu_erf {t_erf*1e3:.0f} us {fl/t_erf/1e9:.0f} TF | gate+residual {t_res*1e3:.0f} us {fl/t_res/1e9:.0f} TF")
+        res[f"gemm_epi_{M}x{K}x{N}"] = dict(plain_us=t_plain * 1e3, tanh_us=t_tanh * 1e3, erf_us=t_erf * 1e3, resid_us=t_res * 1e3)
+    out["block_kernels"] = res
+
+
 def op_overhead():
     x = torch.randn(8, 64, device=DEV, dtype=BF)
     t0 = time.perf_counter()
@@ -248,6 +309,8 @@ if __name__ == "__main__":
         attn_patterns()
     if "attn_perf" in which:
         attn_perf()
+    if "block_kernels" in which:
+        block_kernels_perf()
     if "overhead" in which:
         op_overhead()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
