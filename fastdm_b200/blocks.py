@@ -2,6 +2,7 @@
 
     FluxTransformerBlock        fastdm/model/flux.py:78-178
     FluxSingleTransformerBlock  fastdm/model/flux.py:17-76
+    QwenImageTransformerBlock   fastdm/model/qwenimage.py:16-124
     WanTransformerBlock         fastdm/model/wan.py:19-114   (+ WanAttention, layer/transformer.py:393-535)
 
 Same inputs, outputs and weights (diffusers state-dict names) as the reference classes. The op
@@ -31,16 +32,19 @@ def _mod(scale: torch.Tensor, shift: torch.Tensor) -> Tuple[torch.Tensor, torch.
     return (1 + scale).float().contiguous(), shift.float().contiguous()
 
 
-class FluxTransformerBlock:
-    def __init__(self, sd, prefix, num_attention_heads, attention_head_dim, quant_type=torch.float8_e4m3fn,
-                 device="cuda", eps=1e-6):
-        p, q, dv = prefix, quant_type, device
-        self.heads, self.hd = num_attention_heads, attention_head_dim
+class _JointDiTBlock:
+    """Shared body of the MMDiT double-stream blocks (FLUX double block, Qwen-Image block): two
+    streams (image, text) with their own AdaLN modulation, one joint attention over [text | image],
+    per-stream FFN. Sub-classes only differ in where the weights and the six modulation vectors per
+    stream come from."""
+
+    heads: int
+    hd: int
+    quant_type: object
+    eps: float
+
+    def _load_common(self, sd, p, q, dv, ff_img, ff_txt):
         self.dim = self.heads * self.hd
-        self.quant_type = q
-        self.eps = eps
-        self.norm1_linear = load_linear(sd, [f"{p}.norm1.linear"], None, dv)              # unquantized: flux.py:288
-        self.norm1_context_linear = load_linear(sd, [f"{p}.norm1_context.linear"], None, dv)
         self.qkv = load_linear(sd, [f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], q, dv)
         self.add_qkv_proj = load_linear(sd, [f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], q, dv)
         self.to_out = load_linear(sd, [f"{p}.attn.to_out.0"], q, dv)
@@ -49,32 +53,28 @@ class FluxTransformerBlock:
         self.norm_k_weight = sd[f"{p}.attn.norm_k.weight"].to(dv).contiguous()
         self.norm_added_q_weight = sd[f"{p}.attn.norm_added_q.weight"].to(dv).contiguous()
         self.norm_added_k_weight = sd[f"{p}.attn.norm_added_k.weight"].to(dv).contiguous()
-        self.ff = FeedForward(load_linear(sd, [f"{p}.ff.net.0.proj"], q, dv), load_linear(sd, [f"{p}.ff.net.2"], q, dv))
-        self.ff_context = FeedForward(load_linear(sd, [f"{p}.ff_context.net.0.proj"], q, dv),
-                                      load_linear(sd, [f"{p}.ff_context.net.2"], q, dv))
+        self.ff = FeedForward(load_linear(sd, [f"{p}.{ff_img}.net.0.proj"], q, dv), load_linear(sd, [f"{p}.{ff_img}.net.2"], q, dv))
+        self.ff_context = FeedForward(load_linear(sd, [f"{p}.{ff_txt}.net.0.proj"], q, dv),
+                                      load_linear(sd, [f"{p}.{ff_txt}.net.2"], q, dv))
         self.scale = self.hd ** -0.5
 
-    def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None):
+    def _forward_joint(self, hidden_states, encoder_hidden_states, img_mod, txt_mod, image_rotary_emb):
+        """img_mod / txt_mod: (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), each [B, dim]."""
         B, S_img, d = hidden_states.shape
         S_txt = encoder_hidden_states.shape[1]
         S = S_txt + S_img
         H, hd, qt = self.heads, self.hd, self.quant_type
-        # AdaLN parameters (M = batch GEMMs, unquantized as in the reference)
-        emb = self.norm1_linear.forward(F.silu(temb))
-        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
-        cemb = self.norm1_context_linear.forward(F.silu(temb))
-        c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = cemb.chunk(6, dim=1)
-
+        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = img_mod
+        c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = txt_mod
         hid2 = hidden_states.reshape(B * S_img, d)
         enc2 = encoder_hidden_states.reshape(B * S_txt, d)
-        # norm1 + modulate + quant (normalization.py:191-199) for both streams
+        # norm1 + modulate + quant (normalization.py:191-199 / qwenimage.py:77-82) for both streams
         a, c = _mod(scale_msa, shift_msa)
-        xq = ops.layernorm_modulate_quant(hid2, a, c, S_img, qt, self.eps)
+        xq = Quantized(*ops.layernorm_modulate_quant(hid2, a, c, S_img, qt, self.eps)[:3])
         a, c = _mod(c_scale_msa, c_shift_msa)
-        cq = ops.layernorm_modulate_quant(enc2, a, c, S_txt, qt, self.eps)
-        xq, cq = Quantized(*xq[:3]), Quantized(*cq[:3])
+        cq = Quantized(*ops.layernorm_modulate_quant(enc2, a, c, S_txt, qt, self.eps)[:3])
 
-        # joint [txt | img] qkv buffer: both projections write their rows, no torch.cat (transformer.py:293-295)
+        # joint [txt | img] qkv buffer: both projections write their rows, no torch.cat (transformer.py:293-295, 370-372)
         qkv = torch.empty((B, S, 3 * d), device=hid2.device, dtype=hidden_states.dtype)
         for b in range(B):
             self.add_qkv_proj.forward(cq.rows(b * S_txt, (b + 1) * S_txt), out=qkv[b, :S_txt])
@@ -90,7 +90,7 @@ class FluxTransformerBlock:
         g_msa, g_mlp = gate_msa.float().contiguous(), gate_mlp.float().contiguous()
         cg_msa, cg_mlp = c_gate_msa.float().contiguous(), c_gate_mlp.float().contiguous()
         for b in range(B):
-            # hidden = hidden + gate_msa * to_out(attn)      (flux.py:153-154)
+            # hidden = hidden + gate_msa * to_out(attn)      (flux.py:153-154, qwenimage.py:98-99)
             aq = quantize(attn[b, S_txt:], qt)
             self.to_out.forward(aq, gate=g_msa[b:b + 1], residual=hidden_states[b], rows_per_batch=S_img,
                                 out=new_hidden[b])
@@ -107,6 +107,48 @@ class FluxTransformerBlock:
         self.ff_context.forward(nq, gate=cg_mlp, residual=new_encoder.view(B * S_txt, d), rows_per_batch=S_txt,
                                 out=new_encoder.view(B * S_txt, d))
         return new_encoder, new_hidden
+
+
+class FluxTransformerBlock(_JointDiTBlock):
+    def __init__(self, sd, prefix, num_attention_heads, attention_head_dim, quant_type=torch.float8_e4m3fn,
+                 device="cuda", eps=1e-6):
+        p, q, dv = prefix, quant_type, device
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.quant_type = q
+        self.eps = eps
+        self.norm1_linear = load_linear(sd, [f"{p}.norm1.linear"], None, dv)              # unquantized: flux.py:288
+        self.norm1_context_linear = load_linear(sd, [f"{p}.norm1_context.linear"], None, dv)
+        self._load_common(sd, p, q, dv, "ff", "ff_context")
+
+    def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None):
+        # AdaLN parameters (M = batch GEMMs, unquantized as in the reference)
+        emb = self.norm1_linear.forward(F.silu(temb))
+        cemb = self.norm1_context_linear.forward(F.silu(temb))
+        return self._forward_joint(hidden_states, encoder_hidden_states, emb.chunk(6, dim=1), cemb.chunk(6, dim=1),
+                                   image_rotary_emb)
+
+
+class QwenImageTransformerBlock(_JointDiTBlock):
+    """fastdm/model/qwenimage.py:16-124 (+ Attention.forward_qwen, layer/transformer.py:319-391):
+    img_mod / txt_mod give (shift, scale, gate) x 2 per stream; INT8 W8A8 is the reference's default
+    for this model, FP8 works the same."""
+
+    def __init__(self, sd, prefix, num_attention_heads, attention_head_dim, quant_type=torch.int8, device="cuda",
+                 eps=1e-6, quant_img_txt_mod=False):
+        p, q, dv = prefix, quant_type, device
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.quant_type = q
+        self.eps = eps
+        mq = q if quant_img_txt_mod else None                                            # qwenimage.py:219-220
+        self.img_mod_proj = load_linear(sd, [f"{p}.img_mod.1"], mq, dv)
+        self.txt_mod_proj = load_linear(sd, [f"{p}.txt_mod.1"], mq, dv)
+        self._load_common(sd, p, q, dv, "img_mlp", "txt_mlp")
+
+    def forward(self, hidden_states, encoder_hidden_states, encoder_hidden_states_mask, temb, image_rotary_emb=None,
+                joint_attention_kwargs=None):
+        img = self.img_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)   # mod1 = (shift, scale, gate), mod2 likewise
+        txt = self.txt_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)
+        return self._forward_joint(hidden_states, encoder_hidden_states, img, txt, image_rotary_emb)
 
 
 class FluxSingleTransformerBlock:

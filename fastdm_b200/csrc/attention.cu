@@ -314,9 +314,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           trace_ev(p, tr, 2, 1, t);
           tc_fence_after();
           issue_pv(0, stage_addr(uV), t != 0);
+          trace_ev(p, tr, 2, 4, t);
           tc_commit(o_done(0));
           if (has_next) {
             wait_full(uKn);
+            trace_ev(p, tr, 2, 5, t);
             issue_qk(0, stage_addr(uKn));
             tc_commit(s_full(0));
           }
@@ -469,6 +471,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tc_fence_before();
       mbar_arrive(p_ready(x));
       trace_ev(p, tr, x, 5, t);
+      if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < kTraceTiles)
+        atomicMax((unsigned long long*)&p.trace[(x * 8 + 6) * kTraceTiles + t], (unsigned long long)clock64());
       ++t;
     }
 

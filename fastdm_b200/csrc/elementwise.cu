@@ -773,74 +773,67 @@ __global__ void __launch_bounds__(512) qk_norm_rope_row_kernel(
 // A and C are fp32 [batches, cols]; row r uses batch r / rows_per_batch. Output: quantised y
 // (MODE as above) and/or y itself (y_out may be NULL).
 // ------------------------------------------------------------------------------------------------
+struct Sum2 {
+  float a, b;
+};
+__device__ __forceinline__ Sum2 block_sum2(float a, float b, float* smem /*>=64 floats*/) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int nw = blockDim.x >> 5;
+  if (nw == 1) return {a, b};
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    smem[w] = a;
+    smem[32 + w] = b;
+  }
+  __syncthreads();
+  float x = (l < nw) ? smem[l] : 0.f;
+  float y = (l < nw) ? smem[32 + l] : 0.f;
+  x = warp_sum(x);
+  y = warp_sum(y);
+  __syncthreads();
+  return {x, y};
+}
+
+// One CTA per row (occupancy matters more than re-using the modulation vectors: a multi-row variant
+// that kept mul/add in registers ran at 1 CTA/SM for long rows and was 3x slower); mul/add are read
+// through L1 (identical for every row of a batch). Two block reductions per row: {sum, sum of
+// squares} together -- with an exact second pass only when the variance would be computed by
+// cancellation -- and {min, max} of the modulated row.
 template <typename T, int MODE /*0 fp8, 2 int8 asym, 3 none*/, bool ROUND_STEPS, int VPT>
 __global__ void __launch_bounds__(512) ln_mod_quant_kernel(
     const T* __restrict__ in, const float* __restrict__ A, const float* __restrict__ C,
     uint8_t* __restrict__ out, float* __restrict__ scale, int32_t* __restrict__ azp,
-    T* __restrict__ y_out, int64_t rows, int cols, int64_t in_row_stride, int64_t y_row_stride,
-    int64_t rows_per_batch, int rows_per_cta, float eps) {
-  // grid = (row groups of one batch, batches): all rows of a CTA share the batch's mul/add vectors,
-  // which stay in registers (for rows of <= 4 vectors per thread) while the CTA walks its rows with
-  // the next row's loads already in flight.
-  constexpr bool kCacheAC = VPT <= 4;
+    T* __restrict__ y_out, int cols, int64_t in_row_stride, int64_t y_row_stride,
+    int64_t rows_per_batch, float eps) {
   __shared__ float red[64];
+  const int64_t row = blockIdx.x;
   const int nvec = cols >> 3;
-  const int64_t bidx = blockIdx.y;
-  const int64_t r_begin = bidx * rows_per_batch + (int64_t)blockIdx.x * rows_per_cta;
-  int64_t r_end = r_begin + rows_per_cta;
-  if (r_end > (bidx + 1) * rows_per_batch) r_end = (bidx + 1) * rows_per_batch;
-  if (r_end > rows) r_end = rows;
-  if (r_begin >= r_end) return;
+  const T* src = in + row * in_row_stride;
+  const int64_t bidx = row / rows_per_batch;
   const float* Ar = A ? A + bidx * cols : nullptr;
   const float* Cr = C ? C + bidx * cols : nullptr;
-  auto load_ac = [&](const float* base, int v, float fill, float (&dst)[8]) {
-    if (base) {
-      const float4 x0 = *reinterpret_cast<const float4*>(base + v * 8);
-      const float4 x1 = *reinterpret_cast<const float4*>(base + v * 8 + 4);
-      dst[0] = x0.x; dst[1] = x0.y; dst[2] = x0.z; dst[3] = x0.w;
-      dst[4] = x1.x; dst[5] = x1.y; dst[6] = x1.z; dst[7] = x1.w;
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) dst[j] = fill;
-    }
-  };
-  float ac[kCacheAC ? VPT : 1][8], cc[kCacheAC ? VPT : 1][8];
-  if (kCacheAC) {
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
-      if (v < nvec) {
-        load_ac(Ar, v, 1.f, ac[kCacheAC ? i : 0]);
-        load_ac(Cr, v, 0.f, cc[kCacheAC ? i : 0]);
-      }
-    }
-  }
-  U128 raw[VPT], nxt[VPT];
+  U128 raw[VPT];
+  float sum = 0.f, sumsq = 0.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
-    if (v < nvec) raw[i] = ldg128_stream(in + r_begin * in_row_stride + (int64_t)v * 8);
+    if (v < nvec) {
+      raw[i] = ldg128_stream(src + (int64_t)v * 8);
+      float f[8];
+      unpack8<T>(raw[i], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum += f[j];
+        sumsq = fmaf(f[j], f[j], sumsq);
+      }
+    }
   }
-  for (int64_t row = r_begin; row < r_end; ++row) {
-    if (row + 1 < r_end) {
-#pragma unroll
-      for (int i = 0; i < VPT; ++i) {
-        const int v = threadIdx.x + i * blockDim.x;
-        if (v < nvec) nxt[i] = ldg128_stream(in + (row + 1) * in_row_stride + (int64_t)v * 8);
-      }
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
-      if (v < nvec) {
-        float f[8];
-        unpack8<T>(raw[i], f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += f[j];
-      }
-    }
-    const float mean = block_sum(sum, red) / (float)cols;
+  const Sum2 s2 = block_sum2(sum, sumsq, red);
+  const float inv_n = 1.0f / (float)cols;
+  const float mean = s2.a * inv_n;
+  float var = fmaf(-mean, mean, s2.b * inv_n);
+  if (var < 1e-2f * mean * mean) {  // E[x^2] - mean^2 cancels: redo it centred (row-uniform branch)
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
@@ -851,66 +844,73 @@ __global__ void __launch_bounds__(512) ln_mod_quant_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = f[j] - mean;
-          sq += d * d;
+          sq = fmaf(d, d, sq);
         }
       }
     }
-    const float rstd = rsqrtf(block_sum(sq, red) / (float)cols + eps);
-    float mn = INFINITY, mx = -INFINITY;
+    var = block_sum(sq, red) * inv_n;
+  }
+  const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+  float mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < VPT; ++i) {
-      const int v = threadIdx.x + i * blockDim.x;
-      if (v < nvec) {
-        float f[8];
-        unpack8<T>(raw[i], f);
-        float al[8], cl[8];
-        if (!kCacheAC) {
-          load_ac(Ar, v, 1.f, al);
-          load_ac(Cr, v, 0.f, cl);
-        }
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float f[8];
+      unpack8<T>(raw[i], f);
+      float a[8], c[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float a = kCacheAC ? ac[kCacheAC ? i : 0][j] : al[j];
-          const float c = kCacheAC ? cc[kCacheAC ? i : 0][j] : cl[j];
-          float n = (f[j] - mean) * rstd;
-          if (ROUND_STEPS) {
-            n = round_to<T>(n);
-            if (Ar) n = round_to<T>(__fmul_rn(n, a));
-            if (Cr) n = __fadd_rn(n, c);
-          } else {
-            if (Ar) n = __fmul_rn(n, a);
-            if (Cr) n = __fadd_rn(n, c);
-          }
-          f[j] = round_to<T>(n);
-          mn = fminf(mn, f[j]);
-          mx = fmaxf(mx, f[j]);
-        }
-        raw[i] = pack8<T>(f);
-        if (y_out) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
+      for (int j = 0; j < 8; ++j) {
+        a[j] = 1.f;
+        c[j] = 0.f;
       }
+      if (Ar) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(Ar + v * 8));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(Ar + v * 8 + 4));
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      }
+      if (Cr) {
+        const float4 c0 = __ldg(reinterpret_cast<const float4*>(Cr + v * 8));
+        const float4 c1 = __ldg(reinterpret_cast<const float4*>(Cr + v * 8 + 4));
+        c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float n = (f[j] - mean) * rstd;
+        if (ROUND_STEPS) {
+          n = round_to<T>(n);
+          if (Ar) n = round_to<T>(__fmul_rn(n, a[j]));
+          if (Cr) n = __fadd_rn(n, c[j]);
+        } else {
+          if (Ar) n = __fmul_rn(n, a[j]);
+          if (Cr) n = __fadd_rn(n, c[j]);
+        }
+        f[j] = round_to<T>(n);
+        mn = fminf(mn, f[j]);
+        mx = fmaxf(mx, f[j]);
+      }
+      raw[i] = pack8<T>(f);
+      if (y_out) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
     }
-    if (MODE != 3) {
-      MinMax r = block_minmax(mn, mx, red);
-      const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(r.mn, r.mx, fp8_amax_floor<T>());
-      if (threadIdx.x == 0) {
-        scale[row] = p.scale;
-        if (MODE == 2) azp[row] = p.zp;
-      }
-      uint8_t* dst = out + row * (int64_t)cols;
+  }
+  if (MODE == 3) return;
+  MinMax r = block_minmax(mn, mx, red);
+  const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(r.mn, r.mx, fp8_amax_floor<T>());
+  if (threadIdx.x == 0) {
+    scale[row] = p.scale;
+    if (MODE == 2) azp[row] = p.zp;
+  }
+  uint8_t* dst = out + row * (int64_t)cols;
 #pragma unroll
-      for (int i = 0; i < VPT; ++i) {
-        const int v = threadIdx.x + i * blockDim.x;
-        if (v < nvec) {
-          float f[8];
-          unpack8<T>(raw[i], f);
-          uint32_t lo, hi;
-          quantize8<MODE == 3 ? 0 : MODE>(f, p, lo, hi);
-          stg64(dst + (int64_t)v * 8, lo, hi);
-        }
-      }
+  for (int i = 0; i < VPT; ++i) {
+    const int v = threadIdx.x + i * blockDim.x;
+    if (v < nvec) {
+      float f[8];
+      unpack8<T>(raw[i], f);
+      uint32_t lo, hi;
+      quantize8<MODE == 3 ? 0 : MODE>(f, p, lo, hi);
+      stg64(dst + (int64_t)v * 8, lo, hi);
     }
-#pragma unroll
-    for (int i = 0; i < VPT; ++i) raw[i] = nxt[i];
   }
 }
 
@@ -1168,14 +1168,10 @@ static void launch_lnq(const void* in, const float* A, const float* C, void* out
   int block = (((nvec + 3) / 4 + 31) / 32) * 32;
   if (block > 512) block = 512;
   const int vpt = (nvec + block - 1) / block;
-  // rows per CTA: enough CTAs for ~8 per SM, at most 8 rows each
-  const int64_t batches = (rows + rpb - 1) / rpb;
-  int rpc = 4;
-  while (rpc > 1 && batches * ((rpb + rpc - 1) / rpc) < (int64_t)num_sms() * 16) rpc >>= 1;
-  dim3 g((unsigned)((rpb + rpc - 1) / rpc), (unsigned)batches);
+  const unsigned g = (unsigned)rows;
 #define LNQ(V)                                                                                      \
   ln_mod_quant_kernel<T, MODE, RS, V><<<g, block, 0, st>>>((const T*)in, A, C, (uint8_t*)out, scale, \
-                                                           azp, (T*)y, rows, cols, is, ys, rpb, rpc, eps)
+                                                           azp, (T*)y, cols, is, ys, rpb, eps)
   if (vpt <= 1) LNQ(1);
   else if (vpt <= 2) LNQ(2);
   else if (vpt <= 4) LNQ(4);

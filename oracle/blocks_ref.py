@@ -154,6 +154,39 @@ class FluxTransformerBlockRef:
         return encoder, hidden
 
 
+class QwenImageTransformerBlockRef:
+    """fastdm/model/qwenimage.py:16-124 with Attention.forward_qwen (layer/transformer.py:319-391)."""
+
+    def __init__(self, sd, prefix, heads, head_dim, quant):
+        p = prefix
+        self.dim = heads * head_dim
+        self.eps = 1e-6
+        self.img_mod = QLinearRef(sd, [f"{p}.img_mod.1"])
+        self.txt_mod = QLinearRef(sd, [f"{p}.txt_mod.1"])
+        self.attn = FluxAttentionRef(sd, f"{p}.attn", heads, head_dim, quant, joint=True)  # same op sequence
+        self.img_mlp = FeedForwardRef(sd, f"{p}.img_mlp", quant)
+        self.txt_mlp = FeedForwardRef(sd, f"{p}.txt_mlp", quant)
+
+    @staticmethod
+    def _modulate(x, mod):
+        shift, scale, gate = mod.chunk(3, dim=-1)
+        return x * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1), gate.unsqueeze(1)
+
+    def forward(self, hidden, encoder, temb, rope=None):
+        img_mod1, img_mod2 = self.img_mod.forward(F.silu(temb)).chunk(2, dim=-1)
+        txt_mod1, txt_mod2 = self.txt_mod.forward(F.silu(temb)).chunk(2, dim=-1)
+        img_m, img_gate1 = self._modulate(F.layer_norm(hidden, (self.dim,), eps=self.eps), img_mod1)
+        txt_m, txt_gate1 = self._modulate(F.layer_norm(encoder, (self.dim,), eps=self.eps), txt_mod1)
+        img_attn, txt_attn = self.attn.forward(img_m, txt_m, rope)
+        hidden = hidden + img_gate1 * img_attn
+        encoder = encoder + txt_gate1 * txt_attn
+        img_m2, img_gate2 = self._modulate(F.layer_norm(hidden, (self.dim,), eps=self.eps), img_mod2)
+        hidden = hidden + img_gate2 * self.img_mlp.forward(img_m2)
+        txt_m2, txt_gate2 = self._modulate(F.layer_norm(encoder, (self.dim,), eps=self.eps), txt_mod2)
+        encoder = encoder + txt_gate2 * self.txt_mlp.forward(txt_m2)
+        return encoder, hidden
+
+
 class FluxSingleTransformerBlockRef:
     """fastdm/model/flux.py:17-76 (single-stream block)."""
 
@@ -272,6 +305,22 @@ def flux_double_state_dict(prefix, dim, head_dim, seed, dtype=torch.bfloat16):
     for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
         sd[f"{p}.attn.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g)).to(dtype)
     for ff in ("ff", "ff_context"):
+        _lin(sd, f"{p}.{ff}.net.0.proj", 4 * dim, dim, g)
+        _lin(sd, f"{p}.{ff}.net.2", dim, 4 * dim, g)
+    return sd
+
+
+def qwen_block_state_dict(prefix, dim, head_dim, seed, dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    p = prefix
+    _lin(sd, f"{p}.img_mod.1", 6 * dim, dim, g)
+    _lin(sd, f"{p}.txt_mod.1", 6 * dim, dim, g)
+    for n in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"):
+        _lin(sd, f"{p}.attn.{n}", dim, dim, g)
+    for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        sd[f"{p}.attn.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g)).to(dtype)
+    for ff in ("img_mlp", "txt_mlp"):
         _lin(sd, f"{p}.{ff}.net.0.proj", 4 * dim, dim, g)
         _lin(sd, f"{p}.{ff}.net.2", dim, 4 * dim, g)
     return sd

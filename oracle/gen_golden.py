@@ -231,6 +231,41 @@ def main():
                                           sd_double=sd, sd_single=sd1, enc_out=enc_o, hid_out=hid_o,
                                           single_in=cat, single_out=single_o))
 
+    # --- Qwen-Image block: fastdm/model/qwenimage.py:215-239 (INT8 is the reference default for this model)
+    from fastdm.model.qwenimage import QwenImageTransformerBlock
+    dim, heads, hd = 128, 2, 64
+    g = gen(9)
+    img = torch.randn(1, 96, dim, generator=g).to(BF)
+    txt = torch.randn(1, 32, dim, generator=g).to(BF)
+    temb = torch.randn(1, dim, generator=g).to(BF)
+    rope = torch.rand(128, hd, generator=g).to(BF)
+    for quant, tag in ((torch.int8, "int8"), (torch.float8_e4m3fn, "fp8")):
+        sd = B.qwen_block_state_dict("transformer_blocks.0", dim, hd, seed=14)
+        blk = QwenImageTransformerBlock(dim, heads, hd)
+        c = loader(dict(sd))
+        p = "transformer_blocks.0"
+        c.init_weight([f"{p}.img_mod.1"], blk.img_mod_proj, None)
+        c.init_weight([f"{p}.txt_mod.1"], blk.txt_mod_proj, None)
+        blk.attn.norm_q_weight = c.init_weight([f"{p}.attn.norm_q.weight"])
+        blk.attn.norm_k_weight = c.init_weight([f"{p}.attn.norm_k.weight"])
+        c.init_weight([f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], blk.attn.qkv, quant)
+        c.init_weight([f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], blk.attn.add_qkv_proj, quant)
+        c.init_weight([f"{p}.attn.to_out.0"], blk.attn.to_out, quant)
+        c.init_weight([f"{p}.attn.to_add_out"], blk.attn.to_add_out, quant)
+        blk.attn.norm_added_q_weight = c.init_weight([f"{p}.attn.norm_added_q.weight"])
+        blk.attn.norm_added_k_weight = c.init_weight([f"{p}.attn.norm_added_k.weight"])
+        c.init_weight([f"{p}.img_mlp.net.0.proj"], blk.img_mlp.act_fn.proj, quant)
+        c.init_weight([f"{p}.img_mlp.net.2"], blk.img_mlp.ff_out_proj, quant)
+        c.init_weight([f"{p}.txt_mlp.net.0.proj"], blk.txt_mlp.act_fn.proj, quant)
+        c.init_weight([f"{p}.txt_mlp.net.2"], blk.txt_mlp.ff_out_proj, quant)
+        assert not c.unmatched_tensors
+        enc_o, hid_o = blk.forward(img, txt, None, temb, image_rotary_emb=rope)
+        rb = B.QwenImageTransformerBlockRef(sd, p, heads, hd, quant)
+        enc_r, hid_r = rb.forward(img, txt, temb, rope)
+        ok &= same(enc_o, enc_r) and same(hid_o, hid_r)
+        save(f"block_qwen_{tag}.pt", dict(dim=dim, heads=heads, hd=hd, img=img, txt=txt, temb=temb, rope=rope, sd=sd,
+                                          enc_out=enc_o, hid_out=hid_o))
+
     # --- Wan block: fastdm/model/wan.py:249-281
     dim, heads, hd, ffn = 128, 2, 64, 384
     g = gen(8)

@@ -60,6 +60,17 @@ def test_wan_block_golden(lib, tag, quant):
     check(y, c["y"], "wan block")
 
 
+@pytest.mark.parametrize("tag,quant", [("int8", torch.int8), ("fp8", torch.float8_e4m3fn)])
+def test_qwen_block_golden(lib, tag, quant):
+    from fastdm_b200.blocks import QwenImageTransformerBlock
+
+    c = golden(f"block_qwen_{tag}.pt")
+    blk = QwenImageTransformerBlock(to_dev(c["sd"]), "transformer_blocks.0", c["heads"], c["hd"], quant)
+    enc, hid = blk.forward(c["img"].to(DEV), c["txt"].to(DEV), None, c["temb"].to(DEV), c["rope"].to(DEV))
+    check(enc, c["enc_out"], "qwen block / text stream")
+    check(hid, c["hid_out"], "qwen block / image stream")
+
+
 def test_qlinear_weight_quant_matches_reference_cpu_quant(lib):
     # load-time weight quantisation on the GPU == fastdm/utils/quantization.py on the CPU, bit for bit
     from fastdm_b200.layers import load_linear

@@ -101,3 +101,11 @@ def test_wan_block_golden():
         blk = B.WanTransformerBlockRef(c["sd"], "blocks.0", c["heads"], c["hd"], quant)
         y = blk.forward(c["x"], c["enc"], c["temb"], (c["cos"], c["sin"]))
         assert eq(y, c["y"])
+
+
+def test_qwen_block_golden():
+    for tag, quant in (("int8", torch.int8), ("fp8", torch.float8_e4m3fn)):
+        c = golden(f"block_qwen_{tag}.pt")
+        blk = B.QwenImageTransformerBlockRef(c["sd"], "transformer_blocks.0", c["heads"], c["hd"], quant)
+        enc, hid = blk.forward(c["img"], c["txt"], c["temb"], c["rope"])
+        assert eq(enc, c["enc_out"]) and eq(hid, c["hid_out"])

@@ -18,9 +18,11 @@ names = {0: ["wait_S", "S_ready", "ld_done", "max+resc done", "exp_done", "arriv
 for t in range(8, 20):
     a = [int(tr[0, e, t]) - t0 for e in range(6)]
     bb = [int(tr[1, e, t]) - t0 for e in range(6)]
-    m = [int(tr[2, e, t]) - t0 for e in range(4)]
+    m = [int(tr[2, e, t]) - t0 for e in range(6)]
+    la = int(tr[0, 6, t]) - t0
+    lb = int(tr[1, 6, t]) - t0
     print(f"tile {t:2d} | softA waitS {a[0]:6d} Srdy {a[1]:6d} ld {a[2]-a[1]:4d} max {a[3]-a[2]:4d} exp {a[4]-a[3]:4d} st+arr {a[5]-a[4]:4d} -> {a[5]:6d}"
           f" | softB waitS {bb[0]:6d} Srdy {bb[1]:6d} ld {bb[2]-bb[1]:4d} max {bb[3]-bb[2]:4d} exp {bb[4]-bb[3]:4d} st+arr {bb[5]-bb[4]:4d} -> {bb[5]:6d}"
-          f" | MMA Vrdy {m[0]:6d} P_A {m[1]:6d} issued {m[2]:6d} P_B {m[3]:6d}")
+          f" | MMA Vrdy {m[0]:6d} P_A {m[1]:6d} (last arrive {la:6d}) pv_issued +{m[4]-m[1]:4d} k_rdy +{m[5]-m[1]:4d} qk_issued +{m[2]-m[1]:4d} P_B {m[3]:6d} (last arrive {lb:6d})")
 per = (int(tr[2, 1, 40]) - int(tr[2, 1, 8])) / 32
 print("cycles per KV iteration (2 Q tiles x 128 keys):", per, " -> MMA-ideal 2048")

@@ -12,7 +12,7 @@ int num_sms() { return 148; }
 using namespace fdm;
 using namespace fdm::sm100;
 
-template <int MODE /*0 SS bf16, 1 TS bf16, 2 SS fp8, 3 SS bf16 B MN-major, 4 TS bf16 B MN-major*/>
+template <int MODE /*0 SS bf16, 1 TS bf16, 2 SS fp8, 3 SS bf16 B MN-major, 4 TS bf16 B MN-major, 5/6 attention-like*/>
 __global__ void __launch_bounds__(128, 1) bench(int N, int iters, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -44,6 +44,28 @@ __global__ void __launch_bounds__(128, 1) bench(int N, int iters, long long* out
     mbar_wait(smem_u32(&bar), 0);
     long long t1 = clock64();
     out[0] = t1 - t0;
+    if (MODE >= 5) {
+      // attention-like stream: PV (TS: A = P read from TMEM region X, D = O) followed by QK (SS, D = S).
+      // MODE 5: S aliases X (as in the kernel: P lives over S), MODE 6: S in a different region.
+      const uint32_t idesc_qk = make_idesc(kFmtBF16, kFmtBF16, kAccF32, 128, 128, 0, 0);
+      const uint32_t idesc_pv = make_idesc(kFmtBF16, kFmtBF16, kAccF32, 128, 128, 0, 1);
+      const uint32_t tX = tm, tO = tm + 256, tS = (MODE == 5) ? tm : tm + 128;
+      t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_ts<MmaKind::F16>(tO, tX + ks * 8, make_desc_mnmajor_sw128(b_smem + ks * 2048u, 16384, 1024), idesc_pv, 1);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t off = (uint32_t)(ks / 4) * 16384u + (uint32_t)(ks % 4) * 32u;
+          umma_ss<MmaKind::F16, 1>(tS, make_desc_kmajor_sw128(a_smem + off), make_desc_kmajor_sw128(b_smem + 32768 + off), idesc_qk, ks != 0);
+        }
+      }
+      tc_commit(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), 1);
+      t1 = clock64();
+      out[0] = (t1 - t0) / 2;  // 16 MMAs per iteration, caller divides by 8
+    }
   }
   __syncthreads();
   if (threadIdx.x < 32) tmem_dealloc<1>(tm, 512);
@@ -72,6 +94,8 @@ int main() {
       run<4>("TS bf16 (A tmem, B MN-major)", N, grid);
       run<2>("SS fp8  (K=32)", N, grid);
     }
+    run<5>("PV(TS)+QK(SS), S aliases P", 128, grid);
+    run<6>("PV(TS)+QK(SS), S elsewhere", 128, grid);
   }
   return 0;
 }
