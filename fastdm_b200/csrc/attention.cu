@@ -264,22 +264,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
       const uint32_t tO[2] = {tmem_base + 256u, tmem_base + 384u};
       const uint32_t q_smem[2] = {base + S::kQOff, base + S::kQOff + S::kTileBytes};
+      // descriptors: the start-address field is the low 14 bits (>>4), so stepping inside a tile is an add
+      const uint64_t q_desc[2] = {make_desc_kmajor_sw128(q_smem[0]), make_desc_kmajor_sw128(q_smem[1])};
       auto issue_qk = [&](int x, uint32_t k_smem) {
+        const uint64_t k_desc = make_desc_kmajor_sw128(k_smem);
 #pragma unroll
         for (int ks = 0; ks < HD * ES / 32; ++ks) {  // 32 bytes of head dim per MMA
-          const uint32_t off = (uint32_t)(ks / 4) * (kQTile * 128) + (uint32_t)(ks % 4) * 32u;
-          umma_ss<kKind, 1>(tS[x], make_desc_kmajor_sw128(q_smem[x] + off),
-                            make_desc_kmajor_sw128(k_smem + off), kIdescQK, ks != 0);
+          const uint64_t off = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
+          umma_ss<kKind, 1>(tS[x], q_desc[x] + off, k_desc + off, kIdescQK, ks != 0);
         }
       };
       auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate) {
+        const uint64_t v_desc = make_desc_mnmajor_sw128(v_smem, kKvTile * 128, 1024);
 #pragma unroll
         for (int ks = 0; ks < kKvTile / kKeysPerPV; ++ks) {
           // kKeysPerPV keys = that many 128-byte rows of V; the matching slice of P is 8 TMEM columns
-          const uint64_t bdesc = make_desc_mnmajor_sw128(v_smem + (uint32_t)(ks * kKeysPerPV * 128),
-                                                         kKvTile * 128, 1024);
-          umma_ts<kKind>(tO[x], tS[x] + (uint32_t)ks * 8u, bdesc, kIdescPV,
-                         (accumulate || ks != 0) ? 1u : 0u);
+          umma_ts<kKind>(tO[x], tS[x] + (uint32_t)ks * 8u, v_desc + (uint64_t)((ks * kKeysPerPV * 128) >> 4),
+                         kIdescPV, (accumulate || ks != 0) ? 1u : 0u);
         }
       };
       auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kTileBytes; };
@@ -308,7 +309,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint32_t uV = 2 * t + 1, uKn = 2 * t + 2;
           const uint32_t ph = t & 1u;
           const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+          // both operand tiles of this half-iteration were requested more than an iteration ago: take their
+          // (already satisfied, but ~100-cycle) barrier waits BEFORE blocking on the softmax, so that PV_A
+          // and QK_A go out back to back once P_A arrives
           wait_full(uV);
+          if (has_next) wait_full(uKn);
           trace_ev(p, tr, 2, 0, t);
           mbar_wait(p_ready(0), ph);
           trace_ev(p, tr, 2, 1, t);
@@ -317,7 +322,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           trace_ev(p, tr, 2, 4, t);
           tc_commit(o_done(0));
           if (has_next) {
-            wait_full(uKn);
             trace_ev(p, tr, 2, 5, t);
             issue_qk(0, stage_addr(uKn));
             tc_commit(s_full(0));
