@@ -3,6 +3,7 @@
     FluxTransformerBlock        fastdm/model/flux.py:78-178
     FluxSingleTransformerBlock  fastdm/model/flux.py:17-76
     QwenImageTransformerBlock   fastdm/model/qwenimage.py:16-124
+    JointTransformerBlock       fastdm/model/sd35.py:31-200 (SD3.5, incl. dual attention / context_pre_only)
     WanTransformerBlock         fastdm/model/wan.py:19-114   (+ WanAttention, layer/transformer.py:393-535)
 
 Same inputs, outputs and weights (diffusers state-dict names) as the reference classes. The op
@@ -43,36 +44,48 @@ class _JointDiTBlock:
     quant_type: object
     eps: float
 
-    def _load_common(self, sd, p, q, dv, ff_img, ff_txt):
+    def _load_common(self, sd, p, q, dv, ff_img, ff_txt, context_pre_only=False):
         self.dim = self.heads * self.hd
         self.qkv = load_linear(sd, [f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], q, dv)
         self.add_qkv_proj = load_linear(sd, [f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], q, dv)
         self.to_out = load_linear(sd, [f"{p}.attn.to_out.0"], q, dv)
-        self.to_add_out = load_linear(sd, [f"{p}.attn.to_add_out"], q, dv)
+        self.to_add_out = None if context_pre_only else load_linear(sd, [f"{p}.attn.to_add_out"], q, dv)
         self.norm_q_weight = sd[f"{p}.attn.norm_q.weight"].to(dv).contiguous()
         self.norm_k_weight = sd[f"{p}.attn.norm_k.weight"].to(dv).contiguous()
         self.norm_added_q_weight = sd[f"{p}.attn.norm_added_q.weight"].to(dv).contiguous()
         self.norm_added_k_weight = sd[f"{p}.attn.norm_added_k.weight"].to(dv).contiguous()
         self.ff = FeedForward(load_linear(sd, [f"{p}.{ff_img}.net.0.proj"], q, dv), load_linear(sd, [f"{p}.{ff_img}.net.2"], q, dv))
-        self.ff_context = FeedForward(load_linear(sd, [f"{p}.{ff_txt}.net.0.proj"], q, dv),
-                                      load_linear(sd, [f"{p}.{ff_txt}.net.2"], q, dv))
+        self.ff_context = None if context_pre_only else FeedForward(
+            load_linear(sd, [f"{p}.{ff_txt}.net.0.proj"], q, dv), load_linear(sd, [f"{p}.{ff_txt}.net.2"], q, dv))
         self.scale = self.hd ** -0.5
 
-    def _forward_joint(self, hidden_states, encoder_hidden_states, img_mod, txt_mod, image_rotary_emb):
-        """img_mod / txt_mod: (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), each [B, dim]."""
+    def _forward_joint(self, hidden_states, encoder_hidden_states, img_mod, txt_mod, image_rotary_emb,
+                       dual_mod=None, context_pre_only=False, eps1=None):
+        """img_mod / txt_mod: (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), each [B, dim].
+        SD3.5 extras: `dual_mod` = (shift_msa2, scale_msa2, gate_msa2) runs the image-only second attention
+        (self.attn2_*); `context_pre_only` (last block): txt_mod = (shift, scale), the text stream only feeds
+        k/v and is dropped afterwards; `eps1` overrides the first LayerNorm's eps."""
         B, S_img, d = hidden_states.shape
         S_txt = encoder_hidden_states.shape[1]
         S = S_txt + S_img
         H, hd, qt = self.heads, self.hd, self.quant_type
+        eps1 = self.eps if eps1 is None else eps1
         shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = img_mod
-        c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = txt_mod
+        if context_pre_only:
+            c_shift_msa, c_scale_msa = txt_mod
+            c_gate_msa = c_shift_mlp = c_scale_mlp = c_gate_mlp = None
+        else:
+            c_shift_msa, c_scale_msa, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = txt_mod
         hid2 = hidden_states.reshape(B * S_img, d)
         enc2 = encoder_hidden_states.reshape(B * S_txt, d)
         # norm1 + modulate + quant (normalization.py:191-199 / qwenimage.py:77-82) for both streams
         a, c = _mod(scale_msa, shift_msa)
-        xq = Quantized(*ops.layernorm_modulate_quant(hid2, a, c, S_img, qt, self.eps)[:3])
+        xq = Quantized(*ops.layernorm_modulate_quant(hid2, a, c, S_img, qt, eps1)[:3])
         a, c = _mod(c_scale_msa, c_shift_msa)
         cq = Quantized(*ops.layernorm_modulate_quant(enc2, a, c, S_txt, qt, self.eps)[:3])
+        if dual_mod is not None:   # SD35AdaLayerNormZeroX: the same LayerNorm output, second modulation
+            a, c = _mod(dual_mod[1], dual_mod[0])
+            xq2 = Quantized(*ops.layernorm_modulate_quant(hid2, a, c, S_img, qt, eps1)[:3])
 
         # joint [txt | img] qkv buffer: both projections write their rows, no torch.cat (transformer.py:293-295, 370-372)
         qkv = torch.empty((B, S, 3 * d), device=hid2.device, dtype=hidden_states.dtype)
@@ -86,22 +99,35 @@ class _JointDiTBlock:
         attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale)
 
         new_hidden = torch.empty_like(hidden_states)
-        new_encoder = torch.empty_like(encoder_hidden_states)
+        new_encoder = None if context_pre_only else torch.empty_like(encoder_hidden_states)
         g_msa, g_mlp = gate_msa.float().contiguous(), gate_mlp.float().contiguous()
-        cg_msa, cg_mlp = c_gate_msa.float().contiguous(), c_gate_mlp.float().contiguous()
+        if not context_pre_only:
+            cg_msa, cg_mlp = c_gate_msa.float().contiguous(), c_gate_mlp.float().contiguous()
         for b in range(B):
             # hidden = hidden + gate_msa * to_out(attn)      (flux.py:153-154, qwenimage.py:98-99)
             aq = quantize(attn[b, S_txt:], qt)
             self.to_out.forward(aq, gate=g_msa[b:b + 1], residual=hidden_states[b], rows_per_batch=S_img,
                                 out=new_hidden[b])
-            eq = quantize(attn[b, :S_txt], qt)
-            self.to_add_out.forward(eq, gate=cg_msa[b:b + 1], residual=encoder_hidden_states[b],
-                                    rows_per_batch=S_txt, out=new_encoder[b])
+            if not context_pre_only:
+                eq = quantize(attn[b, :S_txt], qt)
+                self.to_add_out.forward(eq, gate=cg_msa[b:b + 1], residual=encoder_hidden_states[b],
+                                        rows_per_batch=S_txt, out=new_encoder[b])
+        if dual_mod is not None:
+            # hidden = hidden + gate_msa2 * attn2(norm_hidden_states2)      (sd35.py:165-168): image-only attention
+            qkv2 = self.attn2_qkv.forward(xq2).view(B, S_img, 3 * d)
+            for b in range(B):
+                ops.qk_norm_rope_(qkv2[b], self.attn2_norm_q, self.attn2_norm_k, None, H, H, hd, 0, d, 0, self.eps)
+            attn2 = ops.attention(qkv2[:, :, :d], qkv2[:, :, d:2 * d], qkv2[:, :, 2 * d:], H, hd, self.scale)
+            self.attn2_to_out.forward(quantize(attn2.view(B * S_img, d), qt), gate=dual_mod[2].float().contiguous(),
+                                      residual=new_hidden.view(B * S_img, d), rows_per_batch=S_img,
+                                      out=new_hidden.view(B * S_img, d))
         # norm2 + modulate + quant, ff with GELU(tanh) epilogue, gate + residual epilogue (flux.py:156-163)
         a, c = _mod(scale_mlp, shift_mlp)
         nq = Quantized(*ops.layernorm_modulate_quant(new_hidden.view(B * S_img, d), a, c, S_img, qt, self.eps)[:3])
         self.ff.forward(nq, gate=g_mlp, residual=new_hidden.view(B * S_img, d), rows_per_batch=S_img,
                         out=new_hidden.view(B * S_img, d))
+        if context_pre_only:
+            return None, new_hidden
         a, c = _mod(c_scale_mlp, c_shift_mlp)
         nq = Quantized(*ops.layernorm_modulate_quant(new_encoder.view(B * S_txt, d), a, c, S_txt, qt, self.eps)[:3])
         self.ff_context.forward(nq, gate=cg_mlp, residual=new_encoder.view(B * S_txt, d), rows_per_batch=S_txt,
@@ -149,6 +175,44 @@ class QwenImageTransformerBlock(_JointDiTBlock):
         img = self.img_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)   # mod1 = (shift, scale, gate), mod2 likewise
         txt = self.txt_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)
         return self._forward_joint(hidden_states, encoder_hidden_states, img, txt, image_rotary_emb)
+
+
+class JointTransformerBlock(_JointDiTBlock):
+    """SD3 / SD3.5 MMDiT block, fastdm/model/sd35.py:31-200: no RoPE, optional image-only second
+    attention (`use_dual_attention`, SD3.5-medium layers 0-12), `context_pre_only` for the last block."""
+
+    def __init__(self, sd, prefix, num_attention_heads, attention_head_dim, quant_type=torch.float8_e4m3fn,
+                 device="cuda", context_pre_only=False, use_dual_attention=False, eps=1e-6):
+        p, q, dv = prefix, quant_type, device
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.quant_type = q
+        self.eps = eps
+        self.context_pre_only, self.use_dual_attention = context_pre_only, use_dual_attention
+        self.norm1_linear = load_linear(sd, [f"{p}.norm1.linear"], None, dv)            # 6*dim, or 9*dim (dual)
+        self.norm1_context_linear = load_linear(sd, [f"{p}.norm1_context.linear"], None, dv)  # 6*dim, or 2*dim
+        self._load_common(sd, p, q, dv, "ff", "ff_context", context_pre_only)
+        if use_dual_attention:
+            self.attn2_qkv = load_linear(sd, [f"{p}.attn2.to_q", f"{p}.attn2.to_k", f"{p}.attn2.to_v"], q, dv)
+            self.attn2_to_out = load_linear(sd, [f"{p}.attn2.to_out.0"], q, dv)
+            self.attn2_norm_q = sd[f"{p}.attn2.norm_q.weight"].to(dv).contiguous()
+            self.attn2_norm_k = sd[f"{p}.attn2.norm_k.weight"].to(dv).contiguous()
+
+    def forward(self, hidden_states, encoder_hidden_states, temb, joint_attention_kwargs=None):
+        emb = self.norm1_linear.forward(F.silu(temb).to(hidden_states.dtype))
+        dual = None
+        if self.use_dual_attention:      # SD35AdaLayerNormZeroX (normalization.py:45-87): eps 1e-5
+            parts = emb.chunk(9, dim=1)
+            img_mod, dual, eps1 = parts[:6], parts[6:], 1e-5
+        else:
+            img_mod, eps1 = emb.chunk(6, dim=1), 1e-6
+        cemb = self.norm1_context_linear.forward(F.silu(temb).to(hidden_states.dtype))
+        if self.context_pre_only:        # AdaLayerNormContinuous (normalization.py:124-127): scale first, then shift
+            scale, shift = cemb.chunk(2, dim=1)
+            txt_mod = (shift, scale)
+        else:
+            txt_mod = cemb.chunk(6, dim=1)
+        return self._forward_joint(hidden_states, encoder_hidden_states, img_mod, txt_mod, None, dual_mod=dual,
+                                   context_pre_only=self.context_pre_only, eps1=eps1)
 
 
 class FluxSingleTransformerBlock:

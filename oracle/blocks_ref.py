@@ -154,6 +154,83 @@ class FluxTransformerBlockRef:
         return encoder, hidden
 
 
+class JointTransformerBlockRef:
+    """SD3 / SD3.5 block, fastdm/model/sd35.py:31-200 (+ SD35AdaLayerNormZeroX / AdaLayerNormContinuous,
+    fastdm/layer/normalization.py:45-128)."""
+
+    def __init__(self, sd, prefix, heads, head_dim, quant, context_pre_only=False, use_dual_attention=False):
+        p = prefix
+        self.dim = heads * head_dim
+        self.heads, self.head_dim = heads, head_dim
+        self.context_pre_only, self.dual = context_pre_only, use_dual_attention
+        self.norm1 = QLinearRef(sd, [f"{p}.norm1.linear"])
+        self.norm1_context = QLinearRef(sd, [f"{p}.norm1_context.linear"])
+        self.attn = FluxAttentionRef.__new__(FluxAttentionRef)
+        a = self.attn
+        a.heads, a.head_dim, a.inner, a.eps, a.scale, a.joint = heads, head_dim, self.dim, 1e-6, head_dim ** -0.5, True
+        a.qkv = QLinearRef(sd, [f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], quant)
+        a.add_qkv = QLinearRef(sd, [f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], quant)
+        a.to_out = QLinearRef(sd, [f"{p}.attn.to_out.0"], quant)
+        a.to_add_out = None if context_pre_only else QLinearRef(sd, [f"{p}.attn.to_add_out"], quant)
+        a.norm_q, a.norm_k = sd[f"{p}.attn.norm_q.weight"], sd[f"{p}.attn.norm_k.weight"]
+        a.norm_added_q, a.norm_added_k = sd[f"{p}.attn.norm_added_q.weight"], sd[f"{p}.attn.norm_added_k.weight"]
+        if use_dual_attention:
+            self.attn2_qkv = QLinearRef(sd, [f"{p}.attn2.to_q", f"{p}.attn2.to_k", f"{p}.attn2.to_v"], quant)
+            self.attn2_out = QLinearRef(sd, [f"{p}.attn2.to_out.0"], quant)
+            self.attn2_nq, self.attn2_nk = sd[f"{p}.attn2.norm_q.weight"], sd[f"{p}.attn2.norm_k.weight"]
+        self.ff = FeedForwardRef(sd, f"{p}.ff", quant)
+        self.ff_context = None if context_pre_only else FeedForwardRef(sd, f"{p}.ff_context", quant)
+
+    def _joint_attention(self, hidden, encoder):
+        """Attention.forward (layer/transformer.py:232-317) without RoPE; context_pre_only drops to_add_out."""
+        a = self.attn
+        b = hidden.shape[0]
+        q, k, v = a._split_norm(a.qkv.forward(hidden), a.norm_q, a.norm_k, b)
+        eq, ek, ev = a._split_norm(a.add_qkv.forward(encoder), a.norm_added_q, a.norm_added_k, b)
+        q, k, v = torch.cat([eq, q], 1), torch.cat([ek, k], 1), torch.cat([ev, v], 1)
+        o = R.scaled_dot_product_attention(q, k, v, a.heads, a.heads, a.head_dim, scale=a.scale).to(q.dtype)
+        t = encoder.shape[1]
+        eo, o = o[:, :t], o[:, t:]
+        return a.to_out.forward(o), (None if self.context_pre_only else a.to_add_out.forward(eo))
+
+    def forward(self, hidden, encoder, temb):
+        d = self.dim
+        if self.dual:   # SD35AdaLayerNormZeroX.forward
+            emb = self.norm1.forward(F.silu(temb).to(hidden.dtype))
+            (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp, shift_msa2, scale_msa2, gate_msa2) = emb.chunk(9, dim=1)
+            ln = F.layer_norm(hidden, (d,), None, None, 1e-5)
+            n = ln * (1 + scale_msa[:, None]) + shift_msa[:, None]
+            n2 = ln * (1 + scale_msa2[:, None]) + shift_msa2[:, None]
+        else:
+            n, gate_msa, shift_mlp, scale_mlp, gate_mlp = _ada_ln(hidden, temb, self.norm1, 6)
+        if self.context_pre_only:   # AdaLayerNormContinuous.forward
+            emb = self.norm1_context.forward(F.silu(temb).to(encoder.dtype))
+            scale, shift = torch.chunk(emb, 2, dim=1)
+            ne = F.layer_norm(encoder, (d,), None, None, 1e-6) * (1 + scale)[:, None, :] + shift[:, None, :]
+        else:
+            ne, c_gate_msa, c_shift_mlp, c_scale_mlp, c_gate_mlp = _ada_ln(encoder, temb, self.norm1_context, 6)
+        attn, c_attn = self._joint_attention(n, ne)
+        hidden = hidden + gate_msa.unsqueeze(1) * attn
+        if self.dual:
+            b = hidden.shape[0]
+            f = self.attn2_qkv.forward(n2)
+            q, k, v = f[:, :, :d], f[:, :, d:2 * d], f[:, :, 2 * d:]
+            q = R.rms_norm(q.unflatten(-1, (self.heads, -1)).contiguous(), self.attn2_nq, 1e-6).view(b, -1, d)
+            k = R.rms_norm(k.unflatten(-1, (self.heads, -1)).contiguous(), self.attn2_nk, 1e-6).view(b, -1, d)
+            o = R.scaled_dot_product_attention(q, k, v, self.heads, self.heads, self.head_dim, scale=self.head_dim ** -0.5)
+            hidden = hidden + gate_msa2.unsqueeze(1) * self.attn2_out.forward(o.to(q.dtype))
+        n = F.layer_norm(hidden, (d,), None, None, 1e-6)
+        n = n * (1 + scale_mlp[:, None]) + shift_mlp[:, None]
+        hidden = hidden + gate_mlp.unsqueeze(1) * self.ff.forward(n)
+        if self.context_pre_only:
+            return None, hidden
+        encoder = encoder + c_gate_msa.unsqueeze(1) * c_attn
+        ne = F.layer_norm(encoder, (d,), None, None, 1e-6)
+        ne = ne * (1 + c_scale_mlp[:, None]) + c_shift_mlp[:, None]
+        encoder = encoder + c_gate_mlp.unsqueeze(1) * self.ff_context.forward(ne)
+        return encoder, hidden
+
+
 class QwenImageTransformerBlockRef:
     """fastdm/model/qwenimage.py:16-124 with Attention.forward_qwen (layer/transformer.py:319-391)."""
 
@@ -305,6 +382,31 @@ def flux_double_state_dict(prefix, dim, head_dim, seed, dtype=torch.bfloat16):
     for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
         sd[f"{p}.attn.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g)).to(dtype)
     for ff in ("ff", "ff_context"):
+        _lin(sd, f"{p}.{ff}.net.0.proj", 4 * dim, dim, g)
+        _lin(sd, f"{p}.{ff}.net.2", dim, 4 * dim, g)
+    return sd
+
+
+def sd3_block_state_dict(prefix, dim, head_dim, seed, context_pre_only=False, use_dual_attention=False,
+                         dtype=torch.bfloat16):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    p = prefix
+    _lin(sd, f"{p}.norm1.linear", (9 if use_dual_attention else 6) * dim, dim, g)
+    _lin(sd, f"{p}.norm1_context.linear", (2 if context_pre_only else 6) * dim, dim, g)
+    names = ["to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0"]
+    if not context_pre_only:
+        names.append("to_add_out")
+    for n in names:
+        _lin(sd, f"{p}.attn.{n}", dim, dim, g)
+    for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        sd[f"{p}.attn.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g)).to(dtype)
+    if use_dual_attention:
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            _lin(sd, f"{p}.attn2.{n}", dim, dim, g)
+        for n in ("norm_q", "norm_k"):
+            sd[f"{p}.attn2.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g)).to(dtype)
+    for ff in (("ff",) if context_pre_only else ("ff", "ff_context")):
         _lin(sd, f"{p}.{ff}.net.0.proj", 4 * dim, dim, g)
         _lin(sd, f"{p}.{ff}.net.2", dim, 4 * dim, g)
     return sd

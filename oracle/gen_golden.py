@@ -231,6 +231,51 @@ def main():
                                           sd_double=sd, sd_single=sd1, enc_out=enc_o, hid_out=hid_o,
                                           single_in=cat, single_out=single_o))
 
+    # --- SD3.5 blocks (dual attention / plain / context_pre_only): fastdm/model/sd35.py:296-326; batch 2 (CFG)
+    from fastdm.model.sd35 import JointTransformerBlock
+    dim, heads, hd = 128, 2, 64
+    g = gen(10)
+    img = torch.randn(2, 80, dim, generator=g).to(BF)
+    txt = torch.randn(2, 27, dim, generator=g).to(BF)
+    temb = torch.randn(2, dim, generator=g).to(BF)
+    sd3 = {}
+    for name, cpo, dual in (("dual", False, True), ("plain", False, False), ("last", True, False)):
+        quant = torch.float8_e4m3fn
+        sd = B.sd3_block_state_dict("transformer_blocks.0", dim, hd, seed=20 + len(sd3), context_pre_only=cpo,
+                                    use_dual_attention=dual)
+        blk = JointTransformerBlock(dim, heads, hd, context_pre_only=cpo, qk_norm="rms_norm", use_dual_attention=dual)
+        c = loader(dict(sd))
+        p = "transformer_blocks.0"
+        c.init_weight([f"{p}.norm1.linear"], blk.norm1.linear)
+        c.init_weight([f"{p}.norm1_context.linear"], blk.norm1_context.linear)
+        blk.attn.norm_q_weight = c.init_weight([f"{p}.attn.norm_q.weight"])
+        blk.attn.norm_k_weight = c.init_weight([f"{p}.attn.norm_k.weight"])
+        c.init_weight([f"{p}.attn.to_q", f"{p}.attn.to_k", f"{p}.attn.to_v"], blk.attn.qkv, quant)
+        c.init_weight([f"{p}.attn.add_q_proj", f"{p}.attn.add_k_proj", f"{p}.attn.add_v_proj"], blk.attn.add_qkv_proj, quant)
+        c.init_weight([f"{p}.attn.to_out.0"], blk.attn.to_out, quant)
+        if not cpo:
+            c.init_weight([f"{p}.attn.to_add_out"], blk.attn.to_add_out, quant)
+        blk.attn.norm_added_q_weight = c.init_weight([f"{p}.attn.norm_added_q.weight"])
+        blk.attn.norm_added_k_weight = c.init_weight([f"{p}.attn.norm_added_k.weight"])
+        if dual:
+            blk.attn2.norm_q_weight = c.init_weight([f"{p}.attn2.norm_q.weight"])
+            blk.attn2.norm_k_weight = c.init_weight([f"{p}.attn2.norm_k.weight"])
+            c.init_weight([f"{p}.attn2.to_q", f"{p}.attn2.to_k", f"{p}.attn2.to_v"], blk.attn2.qkv, quant)
+            c.init_weight([f"{p}.attn2.to_out.0"], blk.attn2.to_out, quant)
+        c.init_weight([f"{p}.ff.net.0.proj"], blk.ff.act_fn.proj, quant)
+        c.init_weight([f"{p}.ff.net.2"], blk.ff.ff_out_proj, quant)
+        if not cpo:
+            c.init_weight([f"{p}.ff_context.net.0.proj"], blk.ff_context.act_fn.proj, quant)
+            c.init_weight([f"{p}.ff_context.net.2"], blk.ff_context.ff_out_proj, quant)
+        assert not c.unmatched_tensors
+        enc_o, hid_o = blk.forward(img, txt, temb)
+        rb = B.JointTransformerBlockRef(sd, p, heads, hd, quant, cpo, dual)
+        enc_r, hid_r = rb.forward(img, txt, temb)
+        ok &= same(hid_o, hid_r) and (cpo or same(enc_o, enc_r))
+        # weights are regenerated from the seed by oracle.blocks_ref.sd3_block_state_dict (keeps the fixture small)
+        sd3[name] = dict(seed=20 + len(sd3), context_pre_only=cpo, dual=dual, enc_out=enc_o, hid_out=hid_o)
+    save("block_sd3_fp8.pt", dict(dim=dim, heads=heads, hd=hd, img=img, txt=txt, temb=temb, blocks=sd3))
+
     # --- Qwen-Image block: fastdm/model/qwenimage.py:215-239 (INT8 is the reference default for this model)
     from fastdm.model.qwenimage import QwenImageTransformerBlock
     dim, heads, hd = 128, 2, 64

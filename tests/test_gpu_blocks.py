@@ -71,6 +71,25 @@ def test_qwen_block_golden(lib, tag, quant):
     check(hid, c["hid_out"], "qwen block / image stream")
 
 
+@pytest.mark.parametrize("name", ["dual", "plain", "last"])
+def test_sd3_blocks_golden(lib, name):
+    """SD3.5 JointTransformerBlock: dual attention (layers 0-12 of SD3.5-medium), plain, and the
+    context_pre_only last block; batch 2 (CFG), head_dim 64, no RoPE."""
+    from fastdm_b200.blocks import JointTransformerBlock
+
+    c = golden("block_sd3_fp8.pt")
+    blk = c["blocks"][name]
+    sd = B.sd3_block_state_dict("transformer_blocks.0", c["dim"], c["hd"], blk["seed"], blk["context_pre_only"], blk["dual"])
+    m = JointTransformerBlock(to_dev(sd), "transformer_blocks.0", c["heads"], c["hd"], torch.float8_e4m3fn,
+                              context_pre_only=blk["context_pre_only"], use_dual_attention=blk["dual"])
+    enc, hid = m.forward(c["img"].to(DEV), c["txt"].to(DEV), c["temb"].to(DEV))
+    check(hid, blk["hid_out"], f"sd3 {name} / image stream")
+    if blk["context_pre_only"]:
+        assert enc is None
+    else:
+        check(enc, blk["enc_out"], f"sd3 {name} / text stream")
+
+
 def test_qlinear_weight_quant_matches_reference_cpu_quant(lib):
     # load-time weight quantisation on the GPU == fastdm/utils/quantization.py on the CPU, bit for bit
     from fastdm_b200.layers import load_linear

@@ -109,3 +109,14 @@ def test_qwen_block_golden():
         blk = B.QwenImageTransformerBlockRef(c["sd"], "transformer_blocks.0", c["heads"], c["hd"], quant)
         enc, hid = blk.forward(c["img"], c["txt"], c["temb"], c["rope"])
         assert eq(enc, c["enc_out"]) and eq(hid, c["hid_out"])
+
+
+def test_sd3_blocks_golden():
+    c = golden("block_sd3_fp8.pt")
+    for name, blk in c["blocks"].items():
+        sd = B.sd3_block_state_dict("transformer_blocks.0", c["dim"], c["hd"], blk["seed"], blk["context_pre_only"], blk["dual"])
+        ref = B.JointTransformerBlockRef(sd, "transformer_blocks.0", c["heads"], c["hd"], torch.float8_e4m3fn,
+                                         blk["context_pre_only"], blk["dual"])
+        enc, hid = ref.forward(c["img"], c["txt"], c["temb"])
+        assert eq(hid, blk["hid_out"]), name
+        assert (enc is None and blk["enc_out"] is None) or eq(enc, blk["enc_out"]), name
