@@ -312,8 +312,12 @@ def attention_roofline(wl, world, device, pk):
     ms = e0.elapsed_time(e1) / n
     flops = 4.0 * H * S * S * hd
     ach = flops / ms / 1e9
+    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
+    # (profiles/r01_ncu_full_summary.txt): only the N=1 launch shapes were captured.
+    traffic = {("wan", 1): 4.494e9, ("flux", 1): 1.939e8}.get((wl, world))
     return dict(bound="tensor", kernel="attn_fwd_kernel<128,bf16>", achieved=ach, peak=pk["bf16"], unit="TFLOP/s",
-                frac=ach / pk["bf16"], traffic=None, ms_per_launch=ms, flops_per_launch=flops,
+                frac=ach / pk["bf16"], traffic=traffic, traffic_unit="bytes/launch (dram read+write, ncu --set full)",
+                algorithmic_bytes=4.0 * S * H * hd * 2, ms_per_launch=ms, flops_per_launch=flops,
                 peak_source=pk["src"] + ", bf16 burst (kernel timed alone)")
 
 
