@@ -41,17 +41,21 @@ constexpr int kKvTile = 128;  // keys per KV tile (UMMA N of QK^T, K extent of P
 constexpr int kMaxKvTiles = 8192;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
 
-template <int HD, int ES>
+template <int HD, int ES, bool PS, int CG>
 struct AttnSmem {
   static constexpr int kHalves = HD * ES / 128;         // 128-byte column groups per row
   static constexpr int kTileBytes = kKvTile * HD * ES;  // one Q / K / V tile
-  static constexpr int kStages = kTileBytes == 32768 ? 4 : 6;
+  static constexpr int kKvBytes = kTileBytes / CG;      // this CTA's share of a K or V tile (CTA pair: half)
+  static constexpr int kPBytes = PS ? kQTile * kKvTile * ES : 0;  // one P tile staged in shared memory
+  static constexpr int kStages = CG == 2 ? 6 : (PS ? (kTileBytes == 32768 ? 3 : 6) : (kTileBytes == 32768 ? 4 : 6));
   static constexpr int kQOff = 0;
-  static constexpr int kKvOff = 2 * kTileBytes;
-  static constexpr int kBarOff = kKvOff + kStages * kTileBytes;
-  static constexpr int kNumBars = 1 + 2 * kStages + 6;
+  static constexpr int kPOff = 2 * kTileBytes;
+  static constexpr int kKvOff = kPOff + 2 * kPBytes;
+  static constexpr int kBarOff = kKvOff + kStages * kKvBytes;
+  static constexpr int kNumBars = 1 + 2 * kStages + 8;
   static constexpr int kFlagsOff = kBarOff + kNumBars * 8 + 16;
-  static constexpr int kTotal = kFlagsOff + kMaxKvTiles + 1024;
+  static constexpr int kTotal = kFlagsOff + kMaxKvTiles / 8 + 1024;  // one flag bit per KV tile; 1 KB alignment slack
+  static_assert(kTotal <= 232448, "attention: shared-memory layout exceeds 227 KB");
 };
 
 struct AttnParams {
@@ -66,7 +70,7 @@ struct AttnParams {
 };
 
 // debug timeline: trace[(role * 8 + event) * 64 + tile] = clock64(); role 0/1 = softmax warp 0 of
-// Q tile A/B, role 2 = MMA thread. Only CTA (0,0,0) writes, only when a buffer was registered.
+// Q tile A/B, role 2 (and 3) = MMA thread(s). Only CTA (0,0,0) writes, only when a buffer was registered.
 constexpr int kTraceTiles = 64;
 __device__ __forceinline__ void trace_ev(const AttnParams& p, bool on, int role, int ev, uint32_t tile) {
   if (on && tile < kTraceTiles) p.trace[(role * 8 + ev) * kTraceTiles + tile] = clock64();
@@ -85,7 +89,8 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   return DT == kDtF16 ? pack_f16(lo, hi) : pack_bf16(lo, hi);
 }
 
-// per-warpgroup register re-budgeting (the kernel is launched at 168 regs/thread = 65536 / 384)
+// per-warpgroup register re-budgeting: the kernel is launched at 168 regs/thread (64512 in all), so
+// 256 x 208 + 128 x R must not exceed that or setmaxnreg.inc never completes: R <= 88
 template <int N>
 __device__ __forceinline__ void reg_alloc() {
   asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
@@ -154,14 +159,15 @@ __device__ __forceinline__ void ex2_emulated_pair(uint64_t y, float& p0, float& 
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-template <int HD, int DT, int EMU>
+template <int HD, int DT, int EMU, bool PS, int CG>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   constexpr int ES = DT == kDtE4M3 ? 1 : 2;  // operand element size
   constexpr bool F16 = DT == kDtF16;
-  using S = AttnSmem<HD, ES>;
-  extern __shared__ uint8_t smem_raw[];
+  static_assert(CG == 1 || (PS && HD == 128 && ES == 2), "the CTA-pair variant is built for hd 128, 16-bit operands, P in smem");
+  using S = AttnSmem<HD, ES, PS, CG>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw_addr);
@@ -173,9 +179,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto s_full = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + x); };
   auto p_ready = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 2 + x); };
   auto o_done = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 4 + x); };
+  auto s_free = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 6 + x); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S::kBarOff + S::kNumBars * 8);
   uint8_t* flags = smem + S::kFlagsOff;
 
+  // CTA pair (CG == 2): the two CTAs of a cluster own 256 query rows each and issue every MMA together as one
+  // M = 256 tcgen05.mma.cta_group::2 -- each CTA stages only half of every K tile (64 keys) and half of
+  // every V tile (64 head-dim columns), so the K/V ring costs half the shared memory and half the L2 reads.
+  // Rank 0 (the leader) runs the MMA thread; kv_full / s_free / p_ready live in the leader's shared memory.
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  auto lead = [&](uint32_t bar) { return CG == 2 ? mapa_u32(bar, 0) : bar; };
+  auto arrive_lead = [&](uint32_t bar) {  // arrive on the leader CTA's copy of a barrier
+    if (rank == 0) mbar_arrive(bar);
+    else mbar_arrive_remote(bar, 0);
+  };
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 2 * kQTile;
@@ -191,124 +208,227 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(q_full, 1);
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), 1);
+      mbar_init(kv_empty(s), PS ? 2 : 1);  // PS: one commit from each of the two MMA issuers
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(s_full(x), 1);
-      mbar_init(p_ready(x), 128);
       mbar_init(o_done(x), 1);
+      // single CTA: one arrival per softmax thread; CTA pair: one elected arrival per softmax warp of both CTAs
+      mbar_init(p_ready(x), CG == 2 ? 8 : 128);
+      mbar_init(s_free(x), CG == 2 ? 8 : 128);
     }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc<1>(smem_u32(tmem_ptr_smem), 512);
+  if (warp == 9) tmem_alloc<CG>(smem_u32(tmem_ptr_smem), 512);
   if (has_mask) {
-    // which KV tiles does this CTA need at all? (identical answer for all three roles)
-    const int qb_lo = q0 / p.mask_bq;
-    const int qb_hi = min((min(q0 + 2 * kQTile, p.Sq) - 1) / p.mask_bq, p.nbq - 1);
-    for (int j = threadIdx.x; j < p.n_kv_tiles; j += kAttnThreads) {
-      const int kb_lo = (j * kKvTile) / p.mask_bk;
-      const int kb_hi = min((min((j + 1) * kKvTile, p.Sk) - 1) / p.mask_bk, p.nbk - 1);
-      int any = 0;
-      for (int qb = qb_lo; qb <= qb_hi; ++qb)
-        for (int kb = kb_lo; kb <= kb_hi; ++kb) any |= mask_bh[(int64_t)qb * p.nbk + kb];
-      flags[j] = any ? 1 : 0;
+    // which KV tiles does this CTA (pair) need at all? (identical answer for all roles; one bit per tile)
+    const int q0g = (int)(blockIdx.x / CG * CG) * 2 * kQTile;
+    const int qb_lo = q0g / p.mask_bq;
+    const int qb_hi = max(qb_lo, min((min(q0g + 2 * CG * kQTile, p.Sq) - 1) / p.mask_bq, p.nbq - 1));
+    for (int j8 = threadIdx.x; j8 * 8 < p.n_kv_tiles; j8 += kAttnThreads) {
+      uint32_t bits = 0;
+      for (int jj = 0; jj < 8 && j8 * 8 + jj < p.n_kv_tiles; ++jj) {
+        const int j = j8 * 8 + jj;
+        const int kb_lo = (j * kKvTile) / p.mask_bk;
+        const int kb_hi = min((min((j + 1) * kKvTile, p.Sk) - 1) / p.mask_bk, p.nbk - 1);
+        int any = 0;
+        for (int qb = qb_lo; qb <= qb_hi; ++qb)
+          for (int kb = kb_lo; kb <= kb_hi; ++kb) any |= mask_bh[(int64_t)qb * p.nbk + kb];
+        bits |= any ? (1u << jj) : 0u;
+      }
+      flags[j8] = (uint8_t)bits;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();  // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  auto tile_active = [&](int j) -> bool { return !has_mask || flags[j] != 0; };
+  auto tile_active = [&](int j) -> bool { return !has_mask || ((flags[j >> 3] >> (j & 7)) & 1) != 0; };
+  auto next_active = [&](int j) {
+    while (j < p.n_kv_tiles && !tile_active(j)) ++j;
+    return j;
+  };
 
   constexpr uint32_t kFmt = DT == kDtE4M3 ? kFmtE4M3 : (F16 ? kFmtF16 : kFmtBF16);
   constexpr MmaKind kKind = DT == kDtE4M3 ? MmaKind::F8F6F4 : MmaKind::F16;
-  constexpr uint32_t kIdescQK = make_idesc(kFmt, kFmt, kAccF32, kQTile, kKvTile, 0, 0);
-  constexpr uint32_t kIdescPV = make_idesc(kFmt, kFmt, kAccF32, kQTile, HD, 0, 1);
+  constexpr uint32_t kIdescQK = make_idesc(kFmt, kFmt, kAccF32, kQTile * CG, kKvTile, 0, 0);
+  constexpr uint32_t kIdescPV = make_idesc(kFmt, kFmt, kAccF32, kQTile * CG, HD, 0, 1);
   constexpr int kBoxElems = 128 / ES;   // elements per 128-byte swizzled row
   constexpr int kKeysPerPV = 32 / ES;   // keys per P.V tcgen05.mma (K = 32 bytes of operand)
 
   if (warp >= 8) {
-    reg_dealloc<80>();
+    reg_dealloc<88>();
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * S::kTileBytes);
+      if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * CG * S::kTileBytes);
+      const uint32_t q_full_lead = lead(q_full);
 #pragma unroll
       for (int x = 0; x < 2; ++x)
 #pragma unroll
-        for (int hf = 0; hf < S::kHalves; ++hf)
-          tma_load_4d(base + S::kQOff + x * S::kTileBytes + hf * (kQTile * 128), &tmap_q, q_full,
-                      hf * kBoxElems, h, q0 + x * kQTile, b);
+        for (int hf = 0; hf < S::kHalves; ++hf) {
+          const uint32_t dst = base + S::kQOff + x * S::kTileBytes + hf * (kQTile * 128);
+          if (CG == 2) tma_load_4d_cg2(dst, &tmap_q, q_full_lead, hf * kBoxElems, h, q0 + x * kQTile, b);
+          else tma_load_4d(dst, &tmap_q, q_full, hf * kBoxElems, h, q0 + x * kQTile, b);
+        }
       uint32_t u = 0;
-      for (int j = 0; j < p.n_kv_tiles; ++j) {
-        if (!tile_active(j)) continue;
+      auto load_tile = [&](const CUtensorMap* tm, int j) {
+        const int stage = u % S::kStages;
+        const uint32_t parity = ((u / S::kStages) & 1u) ^ 1u;
+        mbar_wait(kv_empty(stage), parity);
+        // the full barrier (the leader's, for a CTA pair) counts the bytes of the whole tile
+        if (rank == 0) mbar_arrive_expect_tx(kv_full(stage), S::kTileBytes);
+        const uint32_t dst = base + S::kKvOff + stage * S::kKvBytes;
+        if (CG == 2) {
+          const uint32_t full_lead = lead(kv_full(stage));
+          if (tm == &tmap_k) {
+            // this CTA's 64 keys of the tile, both 64-element head-dim panels ([64 keys x 128 B] each)
 #pragma unroll
-        for (int kv = 0; kv < 2; ++kv) {
-          const int stage = u % S::kStages;
-          const uint32_t parity = ((u / S::kStages) & 1u) ^ 1u;
-          mbar_wait(kv_empty(stage), parity);
-          mbar_arrive_expect_tx(kv_full(stage), S::kTileBytes);
-          const uint32_t dst = base + S::kKvOff + stage * S::kTileBytes;
+            for (int hf = 0; hf < S::kHalves; ++hf)
+              tma_load_4d_cg2(dst + hf * (kKvTile / 2 * 128), tm, full_lead, hf * kBoxElems, h,
+                              j * kKvTile + (int)rank * (kKvTile / 2), b);
+          } else {
+            // all 128 keys, this CTA's 64 head-dim columns (one [128 keys x 128 B] panel)
+            tma_load_4d_cg2(dst, tm, full_lead, (int)rank * kBoxElems, h, j * kKvTile, b);
+          }
+        } else {
 #pragma unroll
           for (int hf = 0; hf < S::kHalves; ++hf)
-            tma_load_4d(dst + hf * (kKvTile * 128), kv == 0 ? &tmap_k : &tmap_v, kv_full(stage),
-                        hf * kBoxElems, h, j * kKvTile, b);
-          ++u;
+            tma_load_4d(dst + hf * (kKvTile * 128), tm, kv_full(stage), hf * kBoxElems, h, j * kKvTile, b);
+        }
+        ++u;
+      };
+      if (PS) {
+        // ring order = order of first use by the MMA warp: K(0), then K(t+1), V(t) for every active tile t
+        int j = next_active(0);
+        if (j < p.n_kv_tiles) load_tile(&tmap_k, j);
+        while (j < p.n_kv_tiles) {
+          const int jn = next_active(j + 1);
+          if (jn < p.n_kv_tiles) load_tile(&tmap_k, jn);
+          load_tile(&tmap_v, j);
+          j = jn;
+        }
+      } else {
+        for (int j = 0; j < p.n_kv_tiles; ++j) {
+          if (!tile_active(j)) continue;
+          load_tile(&tmap_k, j);
+          load_tile(&tmap_v, j);
         }
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t tS[2] = {tmem_base, tmem_base + 128u};
-      const uint32_t tO[2] = {tmem_base + 256u, tmem_base + 384u};
-      const uint32_t q_smem[2] = {base + S::kQOff, base + S::kQOff + S::kTileBytes};
+  } else if (warp == 9 || (PS && warp == 10)) {
+    // ===================== MMA issuers (the leader CTA's, for a pair) =====================
+    // PS: warp 9 issues for Q tile A, warp 10 for Q tile B. A tcgen05.mma blocks its thread once ~4 are
+    // queued, and the barrier waits + descriptor set-up between two groups of MMAs take ~250 cycles of
+    // dependent instructions: with a single issuing thread the tensor pipe drains during every one of them.
+    // Two threads hide each other's gaps.
+    if (lane == 0 && rank == 0) {
+      // per-Q-tile operands as scalars (x is a run-time value for the two PS issuers)
+      auto tS_of = [&](int x) { return tmem_base + (uint32_t)x * 128u; };
+      auto tO_of = [&](int x) { return tmem_base + 256u + (uint32_t)x * 128u; };
       // descriptors: the start-address field is the low 14 bits (>>4), so stepping inside a tile is an add
-      const uint64_t q_desc[2] = {make_desc_kmajor_sw128(q_smem[0]), make_desc_kmajor_sw128(q_smem[1])};
+      auto q_desc_of = [&](int x) { return make_desc_kmajor_sw128(base + S::kQOff + (uint32_t)x * S::kTileBytes); };
+      auto p_desc_of = [&](int x) { return make_desc_kmajor_sw128(base + S::kPOff + (uint32_t)x * S::kPBytes); };
+      auto commit = [&](uint32_t bar) {
+        if (CG == 2) tc_commit_cg2(bar, 0b11);  // the same barrier in both CTAs of the pair
+        else tc_commit(bar);
+      };
       auto issue_qk = [&](int x, uint32_t k_smem) {
         const uint64_t k_desc = make_desc_kmajor_sw128(k_smem);
+        const uint64_t q_desc = q_desc_of(x);
+        const uint32_t tS = tS_of(x);
 #pragma unroll
         for (int ks = 0; ks < HD * ES / 32; ++ks) {  // 32 bytes of head dim per MMA
           const uint64_t off = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
-          umma_ss<kKind, 1>(tS[x], q_desc[x] + off, k_desc + off, kIdescQK, ks != 0);
+          // a CTA of a pair holds kKvTile / 2 keys per head-dim panel
+          const uint64_t koff = (uint64_t)(((ks / 4) * (kKvTile / CG * 128) + (ks % 4) * 32) >> 4);
+          umma_ss<kKind, CG>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
         }
       };
       auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate) {
         const uint64_t v_desc = make_desc_mnmajor_sw128(v_smem, kKvTile * 128, 1024);
+        const uint64_t p_desc = p_desc_of(x);
+        const uint32_t tS = tS_of(x), tO = tO_of(x);
 #pragma unroll
         for (int ks = 0; ks < kKvTile / kKeysPerPV; ++ks) {
-          // kKeysPerPV keys = that many 128-byte rows of V; the matching slice of P is 8 TMEM columns
-          umma_ts<kKind>(tO[x], tS[x] + (uint32_t)ks * 8u, v_desc + (uint64_t)((ks * kKeysPerPV * 128) >> 4),
-                         kIdescPV, (accumulate || ks != 0) ? 1u : 0u);
+          // kKeysPerPV keys = that many 128-byte rows of V; the matching slice of P is 32 bytes of its
+          // K-major rows in shared memory (PS) or 8 TMEM columns
+          const uint64_t voff = (uint64_t)((ks * kKeysPerPV * 128) >> 4);
+          const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
+          if (PS) {
+            const uint64_t poff = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
+            umma_ss<kKind, CG>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
+          } else {
+            umma_ts<kKind>(tO, tS + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
+          }
         }
       };
-      auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kTileBytes; };
+      auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kKvBytes; };
       auto wait_full = [&](uint32_t u) {
         mbar_wait(kv_full(u % S::kStages), (u / S::kStages) & 1u);
         tc_fence_after();
       };
+      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
 
-      // active tiles are numbered t = 0,1,...; K(t) is ring slot 2t, V(t) is ring slot 2t+1
-      int j = 0;
-      while (j < p.n_kv_tiles && !tile_active(j)) ++j;
+      int j = next_active(0);
       if (j < p.n_kv_tiles) {
         mbar_wait(q_full, 0);
         tc_fence_after();
         wait_full(0);
+        if (PS) {
+          // P travels through shared memory, so S_X is free again as soon as the softmax warps hold it in
+          // registers: QK_X(t+1) is issued ahead of PV_X(t) and the only per-tile dependency chain left is
+          // the softmax itself. Ring items (order of first use): K(0) | K(t+1), V(t) | ...; each issuer
+          // releases a stage on its own, the stage's empty barrier counts both.
+          const int x = warp - 9;
+          const int role = 2 + x;
+          issue_qk(x, stage_addr(0));
+          commit(s_full(x));
+          commit(kv_empty(0));
+          uint32_t t = 0, u = 1;
+          while (true) {
+            const int jn = next_active(j + 1);
+            const bool has_next = jn < p.n_kv_tiles;
+            const uint32_t uK = u, uV = has_next ? u + 1 : u;
+            const uint32_t ph = t & 1u;
+            if (has_next) {
+              wait_full(uK);
+              mbar_wait(s_free(x), ph);
+              tc_fence_after();
+              trace_ev(p, tr, role, 0, t);
+              issue_qk(x, stage_addr(uK));
+              commit(s_full(x));
+              commit(kv_empty(uK % S::kStages));
+              trace_ev(p, tr, role, 1, t);
+            }
+            wait_full(uV);
+            mbar_wait(p_ready(x), ph);
+            tc_fence_after();
+            trace_ev(p, tr, role, 2, t);
+            issue_pv(x, stage_addr(uV), t != 0);
+            commit(o_done(x));
+            commit(kv_empty(uV % S::kStages));
+            trace_ev(p, tr, role, 3, t);
+            if (!has_next) break;
+            u += 2;
+            j = jn;
+            ++t;
+          }
+        } else {
         issue_qk(0, stage_addr(0));
-        tc_commit(s_full(0));
+        commit(s_full(0));
         issue_qk(1, stage_addr(0));
-        tc_commit(s_full(1));
-        tc_commit(kv_empty(0));
+        commit(s_full(1));
+        commit(kv_empty(0));
         uint32_t t = 0;
+        // active tiles are numbered t = 0,1,...; K(t) is ring slot 2t, V(t) is ring slot 2t+1
         while (true) {
-          int jn = j + 1;
-          while (jn < p.n_kv_tiles && !tile_active(jn)) ++jn;
+          const int jn = next_active(j + 1);
           const bool has_next = jn < p.n_kv_tiles;
           const uint32_t uV = 2 * t + 1, uKn = 2 * t + 2;
           const uint32_t ph = t & 1u;
-          const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
           // both operand tiles of this half-iteration were requested more than an iteration ago: take their
           // (already satisfied, but ~100-cycle) barrier waits BEFORE blocking on the softmax, so that PV_A
           // and QK_A go out back to back once P_A arrives
@@ -320,25 +440,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tc_fence_after();
           issue_pv(0, stage_addr(uV), t != 0);
           trace_ev(p, tr, 2, 4, t);
-          tc_commit(o_done(0));
+          commit(o_done(0));
           if (has_next) {
             trace_ev(p, tr, 2, 5, t);
             issue_qk(0, stage_addr(uKn));
-            tc_commit(s_full(0));
+            commit(s_full(0));
           }
           trace_ev(p, tr, 2, 2, t);
           mbar_wait(p_ready(1), ph);
           trace_ev(p, tr, 2, 3, t);
           tc_fence_after();
           issue_pv(1, stage_addr(uV), t != 0);
-          tc_commit(o_done(1));
-          tc_commit(kv_empty(uV % S::kStages));
+          commit(o_done(1));
+          commit(kv_empty(uV % S::kStages));
           if (!has_next) break;
           issue_qk(1, stage_addr(uKn));
-          tc_commit(s_full(1));
-          tc_commit(kv_empty(uKn % S::kStages));
+          commit(s_full(1));
+          commit(kv_empty(uKn % S::kStages));
           j = jn;
           ++t;
+        }
         }
       }
     }
@@ -354,6 +475,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = (uint32_t)(lane_group * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + (uint32_t)(x * 128);
     const uint32_t tO = tmem_base + lane_off + 256u + (uint32_t)(x * 128);
+    // this thread's row of the K-major, 128B-swizzled P tile in shared memory (PS)
+    const uint32_t p_row = base + S::kPOff + (uint32_t)x * S::kPBytes + (uint32_t)row_in_tile * 128u;
+    const uint32_t p_sw = (uint32_t)(row_in_tile & 7);
     const int8_t* mask_row = nullptr;
     if (has_mask) mask_row = mask_bh + (int64_t)min(row / p.mask_bq, p.nbq - 1) * p.nbk;
 
@@ -385,13 +509,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       };
 
-      // ---- S row -> registers (one TMEM read; the softmax warpgroups run at 216 registers) ----
+      // ---- S row -> registers (one TMEM read; the softmax warpgroups run at 208 registers) ----
       uint32_t s0[32], s1[32], s2[32], s3[32];
       tmem_ld_32x32(tS, s0);
       tmem_ld_32x32(tS + 32u, s1);
       tmem_ld_32x32(tS + 64u, s2);
       tmem_ld_32x32(tS + 96u, s3);
       tmem_ld_wait();
+      if (PS) {
+        // S_X is in registers: the MMA warp may overwrite it with the next tile's scores right away
+        tc_fence_before();
+        if (CG == 2) {
+          __syncwarp();
+          if (lane == 0) arrive_lead(s_free(x));
+        } else {
+          mbar_arrive(s_free(x));
+        }
+      }
       trace_ev(p, tr, x, 2, t);
       apply_mask(s0, 0);
       apply_mask(s1, 1);
@@ -421,7 +555,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
       trace_ev(p, tr, x, 3, t);
-      // ---- P = exp2(S*scale - m), packed 2 per column over the first 64 columns of S_X ----
+      // the shared-memory P tile is read by PV_X(t-1) until o_done(x) completes its phase
+      if (PS && t > 0) mbar_wait(o_done(x), (t - 1) & 1u);
+      // ---- P = exp2(S*scale - m): over the first columns of S_X in TMEM, or into the P tile in smem ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 4 independent packed partial row sums
@@ -449,11 +585,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
         if (DT == kDtE4M3) {
-          // P -> e4m3, unscaled (the reference's fp8 semantics), 4 keys per TMEM column
+          // P -> e4m3, unscaled (the reference's fp8 semantics), 4 keys per 32-bit word
           uint32_t p8[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) p8[i] = cvt_e4m3x4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
-          tmem_st_32x8(tS + (uint32_t)(c * 8), p8);
+          if (PS) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+              sts128(p_row + ((((uint32_t)(c * 2 + q)) ^ p_sw) << 4), p8[4 * q], p8[4 * q + 1], p8[4 * q + 2], p8[4 * q + 3]);
+          } else {
+            tmem_st_32x8(tS + (uint32_t)(c * 8), p8);
+          }
+        } else if (PS) {
+          // 32 keys = 64 bytes = four 16-byte chunks of this row in panel c/2 (64 keys per 128-byte row)
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(p_row + (uint32_t)((c >> 1) * (kQTile * 128)) + ((((uint32_t)((c & 1) * 4 + q)) ^ p_sw) << 4),
+                   pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         } else {
           tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
         }
@@ -471,9 +619,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         l_run += (m_run == -INFINITY) ? 0.f : (a0 + a1) + (b0 + b1);
       }
       trace_ev(p, tr, x, 4, t);
+      if (PS) fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core's reads
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_ready(x));
+      if (CG == 2) {
+        __syncwarp();
+        if (lane == 0) arrive_lead(p_ready(x));
+      } else {
+        mbar_arrive(p_ready(x));
+      }
       trace_ev(p, tr, x, 5, t);
       if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < kTraceTiles)
         atomicMax((unsigned long long*)&p.trace[(x * 8 + 6) * kTraceTiles + t], (unsigned long long)clock64());
@@ -514,28 +668,71 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();  // neither CTA's shared memory / TMEM goes away while the pair is still working
   if (warp == 9) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, 512);
+    tmem_dealloc<CG>(tmem_base, 512);
   }
+}
+
+template <int HD, int DT, int EMU, bool PS, int CG>
+static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const AttnParams& p, cudaStream_t st) {
+  using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2, PS, CG>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  FDM_CUDA(cudaGetDevice(&dev));
+  auto kern = attn_fwd_kernel<HD, DT, EMU, PS, CG>;
+  if (!attr_set[dev]) {
+    FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    attr_set[dev] = true;
+  }
+  const unsigned nq = (unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((nq + CG - 1) / CG * CG, (unsigned)p.H, (unsigned)p.B);  // whole CTA pairs
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FDM_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p));
+  FDM_LAUNCH_CHECK("attn_fwd kernel launch");
+  return FDM_OK;
+}
+
+// experiment knobs: FDM_ATTN_PSMEM=0 keeps P in TMEM (aliasing S) instead of staging it through shared
+// memory; FDM_ATTN_CG=1 runs single CTAs instead of CTA pairs (hd 128, 16-bit operands)
+static int attn_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static bool attn_pair_setting() {
+  static int v = attn_env("FDM_ATTN_CG", 2);
+  return v == 2;
+}
+// CTA pairs pay off once the K/V loop is long enough to amortise the cluster set-up and there are at least
+// two 256-row query blocks to pair (cross-attention onto 512 text tokens stays on single CTAs)
+static bool attn_use_pair(int64_t Sq, int64_t Sk) {
+  return attn_pair_setting() && Sk >= 8 * kKvTile && Sq > 2 * kQTile;
+}
+static bool attn_psmem_setting() {
+  static int v = attn_env("FDM_ATTN_PSMEM", 0);
+  return v != 0;
 }
 
 template <int HD, int DT, int EMU>
 static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const AttnParams& p, cudaStream_t st) {
-  using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2>;
-  static bool attr_set[64] = {};
-  int dev = 0;
-  FDM_CUDA(cudaGetDevice(&dev));
-  if (!attr_set[dev]) {
-    FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DT, EMU>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  S::kTotal));
-    attr_set[dev] = true;
+  if constexpr (HD == 128 && DT != kDtE4M3) {
+    if (attn_use_pair(p.Sq, p.Sk)) return launch_attn_p<HD, DT, EMU, true, 2>(tq, tk, tv, p, st);
   }
-  dim3 grid((unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile)), (unsigned)p.H, (unsigned)p.B);
-  attn_fwd_kernel<HD, DT, EMU><<<grid, kAttnThreads, S::kTotal, st>>>(tq, tk, tv, p);
-  FDM_LAUNCH_CHECK("attn_fwd kernel launch");
-  return FDM_OK;
+  return attn_psmem_setting() ? launch_attn_p<HD, DT, EMU, true, 1>(tq, tk, tv, p, st)
+                              : launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st);
 }
 
 // how many of every 32 exponentials run on the FMA pipe instead of MUFU (tuning knob; the default is
@@ -562,11 +759,11 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 }
 
 static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,
-                         int64_t batch_stride, int64_t token_stride, int es) {
-  // dims innermost first: d, head, token, batch; one box = 128 rows x 128 bytes
+                         int64_t batch_stride, int64_t token_stride, int es, int box_rows = 128) {
+  // dims innermost first: d, head, token, batch; one box = box_rows rows x 128 bytes
   uint64_t dims[4] = {(uint64_t)hd, (uint64_t)H, (uint64_t)S, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)hd * es, (uint64_t)token_stride * es, (uint64_t)batch_stride * es};
-  uint32_t box[4] = {(uint32_t)(128 / es), 1, 128, 1};
+  uint32_t box[4] = {(uint32_t)(128 / es), 1, (uint32_t)box_rows, 1};
   return make_tmap(out, es == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, ptr,
                    dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
@@ -577,7 +774,7 @@ using namespace fdm;
 
 static long long* g_attn_trace = nullptr;
 extern "C" int fdm_debug_set_attn_trace(void* device_buffer) {
-  g_attn_trace = (long long*)device_buffer;  // 3 roles x 8 events x 64 tiles x int64, or NULL to disable
+  g_attn_trace = (long long*)device_buffer;  // 4 roles x 8 events x 64 tiles x int64, or NULL to disable
   return FDM_OK;
 }
 
@@ -642,7 +839,9 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   }
   rc = make_qkv_tmap(&tq, q, B, Sq, H, hd, q_bs, q_ts, es);
   if (rc) return rc;
-  rc = make_qkv_tmap(&tk, k, B, Sk, H, hd, k_bs, k_ts, es);
+  // a CTA pair splits every K tile by keys: 64-row boxes
+  const bool pair = hd == 128 && es == 2 && attn_use_pair(Sq, Sk);
+  rc = make_qkv_tmap(&tk, k, B, Sk, H, hd, k_bs, k_ts, es, pair ? 64 : 128);
   if (rc) return rc;
   rc = make_qkv_tmap(&tv, v, B, Sk, H, hd, v_bs, v_ts, es);
   if (rc) return rc;

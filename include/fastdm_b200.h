@@ -206,7 +206,7 @@ int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o, const int
                  int64_t o_token_stride, int mask_bq, int mask_bk, float scale, int qkv_dtype,
                  void* stream);
 
-/* Debug aid (not part of the reference API): register a device buffer of 3*8*64 int64 that CTA
+/* Debug aid (not part of the reference API): register a device buffer of 4*8*64 int64 that CTA
  * (0,0,0) of every following fdm_attn_fwd launch fills with clock64() stamps of its pipeline events
  * (tools/attn_trace.py prints the timeline); NULL disables it. */
 int fdm_debug_set_attn_trace(void* device_buffer);

@@ -417,7 +417,7 @@ def test_attention_strided_views_of_fused_qkv(ops):
 
 
 @pytest.mark.parametrize("geom", [(128, 64), (64, 128), (128, 128), (64, 64)])
-@pytest.mark.parametrize("shape", [(1, 900, 900, 3, 128), (2, 333, 515, 2, 64)])
+@pytest.mark.parametrize("shape", [(1, 900, 900, 3, 128), (2, 333, 515, 2, 64), (1, 1300, 2100, 2, 128)])
 def test_sparse_attention_random_block_masks(ops, geom, shape):
     bq, bk = geom
     b, sq, sk, h, hd = shape
@@ -437,6 +437,28 @@ def test_sparse_attention_random_block_masks(ops, geom, shape):
     ref = attn_oracle(q, k, v, h, hd, hd ** -0.5, mask, bq, bk)
     assert (y.cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
     assert float(y[:, : min(bq, sq)].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("hd", [128, 64])
+def test_sparse_attention_banded_mask_skips_tiles(ops, hd):
+    """Radial-style band: most KV tiles are inactive for a given 256/512-row query block, so the active-tile
+    list (shared by both CTAs of a pair for hd 128) and the K/V ring order are exercised."""
+    b, sq, sk, h, bq, bk = 1, 2300, 4100, 2, 128, 64
+    g = torch.Generator().manual_seed(hd)
+    q = torch.randn(b, sq, h * hd, generator=g).to(BF)
+    k = torch.randn(b, sk, h * hd, generator=g).to(BF)
+    v = torch.randn(b, sk, h * hd, generator=g).to(BF)
+    nbq, nbk = -(-sq // bq), -(-sk // bk)
+    qi = torch.arange(nbq).view(-1, 1) * bq
+    kj = torch.arange(nbk).view(1, -1) * bk
+    band = ((kj - 2 * qi).abs() <= 300) | (kj < 64)            # diagonal band + an "attention sink" column block
+    mask = band.to(torch.int8).expand(b, h, nbq, nbk).contiguous()
+    mask[:, 1, 5, :] = 0                                          # one fully masked query block in head 1
+    y = ops.sparse_scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), h, h, hd, scale=hd ** -0.5,
+                                                sparse_mask=mask.to(DEV), block_q=bq, block_k=bk)
+    ref = attn_oracle(q, k, v, h, hd, hd ** -0.5, mask, bq, bk)
+    assert (y.cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
+    assert float(y[:, 5 * bq:6 * bq, hd:].abs().max()) == 0.0
 
 
 def test_sparse_attention_all_ones_equals_dense(ops):

@@ -1,4 +1,8 @@
-"""Prints the intra-CTA timeline of the attention kernel (clock64 stamps of CTA 0) -- debug aid."""
+"""Prints the intra-CTA timeline of the attention kernel (clock64 stamps of CTA 0) -- debug aid.
+
+    python tools/attn_trace.py            # hd 128 bf16: CTA pairs, P through shared memory, two MMA issuers
+    FDM_ATTN_CG=1 python tools/attn_trace.py   # single CTA, P in TMEM, one MMA issuer (legacy event meaning)
+"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fastdm_b200 import _lib, ops
@@ -7,22 +11,26 @@ b, s, h, hd = 1, 8704, 24, 128
 q, k, v = (torch.randn(b, s, h * hd, device="cuda", dtype=torch.bfloat16) for _ in range(3))
 for _ in range(2):
     ops.scaled_dot_product_attention(q, k, v, h, h, hd)
-buf = torch.zeros(3 * 8 * 64, dtype=torch.int64, device="cuda")
+buf = torch.zeros(4 * 8 * 64, dtype=torch.int64, device="cuda")
 lib.fdm_debug_set_attn_trace(buf.data_ptr())
 ops.scaled_dot_product_attention(q, k, v, h, h, hd)
 torch.cuda.synchronize()
 lib.fdm_debug_set_attn_trace(None)
-tr = buf.cpu().view(3, 8, 64)
-t0 = int(tr[2, 0, 0])
-names = {0: ["wait_S", "S_ready", "ld_done", "max+resc done", "exp_done", "arrived"], 1: None, 2: ["V_ready", "P_A ready", "issued PV_A,QK_A", "P_B ready"]}
+tr = buf.cpu().view(4, 8, 64)
+pair = os.environ.get("FDM_ATTN_CG", "2") == "2"
+t0 = int(tr[0, 0, 0])
 for t in range(8, 20):
     a = [int(tr[0, e, t]) - t0 for e in range(6)]
     bb = [int(tr[1, e, t]) - t0 for e in range(6)]
-    m = [int(tr[2, e, t]) - t0 for e in range(6)]
-    la = int(tr[0, 6, t]) - t0
-    lb = int(tr[1, 6, t]) - t0
-    print(f"tile {t:2d} | softA waitS {a[0]:6d} Srdy {a[1]:6d} ld {a[2]-a[1]:4d} max {a[3]-a[2]:4d} exp {a[4]-a[3]:4d} st+arr {a[5]-a[4]:4d} -> {a[5]:6d}"
-          f" | softB waitS {bb[0]:6d} Srdy {bb[1]:6d} ld {bb[2]-bb[1]:4d} max {bb[3]-bb[2]:4d} exp {bb[4]-bb[3]:4d} st+arr {bb[5]-bb[4]:4d} -> {bb[5]:6d}"
-          f" | MMA Vrdy {m[0]:6d} P_A {m[1]:6d} (last arrive {la:6d}) pv_issued +{m[4]-m[1]:4d} k_rdy +{m[5]-m[1]:4d} qk_issued +{m[2]-m[1]:4d} P_B {m[3]:6d} (last arrive {lb:6d})")
-per = (int(tr[2, 1, 40]) - int(tr[2, 1, 8])) / 32
+    line = (f"tile {t:2d} | softA waitS {a[0]:6d} Srdy {a[1]:6d} ld {a[2]-a[1]:4d} max {a[3]-a[2]:4d} exp {a[4]-a[3]:4d} st+arr {a[5]-a[4]:4d} -> {a[5]:6d}"
+            f" | softB waitS {bb[0]:6d} Srdy {bb[1]:6d} ld {bb[2]-bb[1]:4d} max {bb[3]-bb[2]:4d} exp {bb[4]-bb[3]:4d} st+arr {bb[5]-bb[4]:4d} -> {bb[5]:6d}")
+    if pair:
+        for r, nm in ((2, "mmaA"), (3, "mmaB")):
+            m = [int(tr[r, e, t]) - t0 for e in range(4)]
+            line += f" | {nm} qk_go {m[0]:6d} +{m[1]-m[0]:4d} pv_go {m[2]:6d} +{m[3]-m[2]:4d}"
+    else:
+        m = [int(tr[2, e, t]) - t0 for e in range(6)]
+        line += f" | MMA Vrdy {m[0]:6d} P_A {m[1]:6d} pv_issued +{m[4]-m[1]:4d} qk_issued +{m[2]-m[1]:4d} P_B {m[3]:6d}"
+    print(line)
+per = (int(tr[0, 1, 40]) - int(tr[0, 1, 8])) / 32
 print("cycles per KV iteration (2 Q tiles x 128 keys):", per, " -> MMA-ideal 2048")
