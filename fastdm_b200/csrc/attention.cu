@@ -72,8 +72,13 @@ struct AttnParams {
 // debug timeline: trace[(role * 8 + event) * 64 + tile] = clock64(); role 0/1 = softmax warp 0 of
 // Q tile A/B, role 2 (and 3) = MMA thread(s). Only CTA (0,0,0) writes, only when a buffer was registered.
 constexpr int kTraceTiles = 64;
-__device__ __forceinline__ void trace_ev(const AttnParams& p, bool on, int role, int ev, uint32_t tile) {
-  if (on && tile < kTraceTiles) p.trace[(role * 8 + ev) * kTraceTiles + tile] = clock64();
+// (the stamps are compiled into a separate TRACE instantiation of the kernel: even predicated off they cost
+// the production kernel 5-15 %)
+template <bool TRACE>
+__device__ __forceinline__ void trace_ev_t(const AttnParams& p, bool on, int role, int ev, uint32_t tile) {
+  if constexpr (TRACE) {
+    if (on && tile < kTraceTiles) p.trace[(role * 8 + ev) * kTraceTiles + tile] = clock64();
+  }
 }
 
 __device__ __forceinline__ float ex2(float x) {
@@ -159,7 +164,7 @@ __device__ __forceinline__ void ex2_emulated_pair(uint64_t y, float& p0, float& 
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-template <int HD, int DT, int EMU, bool PS, int CG>
+template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -198,7 +203,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int q0 = blockIdx.x * 2 * kQTile;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const bool has_mask = p.mask != nullptr;
+  constexpr bool has_mask = MASKED;  // a block mask was passed (p.mask != nullptr)
+  auto trace_ev = [&](const AttnParams& pp, bool on, int role, int ev, uint32_t tile) { trace_ev_t<TRACE>(pp, on, role, ev, tile); };
   const int8_t* mask_bh = has_mask ? p.mask + ((int64_t)b * p.H + h) * p.nbq * p.nbk : nullptr;
 
   if (warp == 8 && lane == 0) {
@@ -208,7 +214,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(q_full, 1);
     for (int s = 0; s < S::kStages; ++s) {
       mbar_init(kv_full(s), 1);
-      mbar_init(kv_empty(s), PS ? 2 : 1);  // PS: one commit from each of the two MMA issuers
+      mbar_init(kv_empty(s), 1);
     }
     for (int x = 0; x < 2; ++x) {
       mbar_init(s_full(x), 1);
@@ -318,13 +324,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
     __syncwarp();
-  } else if (warp == 9 || (PS && warp == 10)) {
-    // ===================== MMA issuers (the leader CTA's, for a pair) =====================
-    // PS: warp 9 issues for Q tile A, warp 10 for Q tile B. A tcgen05.mma blocks its thread once ~4 are
-    // queued, and the barrier waits + descriptor set-up between two groups of MMAs take ~250 cycles of
-    // dependent instructions: with a single issuing thread the tensor pipe drains during every one of them.
-    // Two threads hide each other's gaps.
-    if (lane == 0 && rank == 0) {
+  } else if (warp == 9) {
+    // ===================== MMA issuer (the leader CTA's, for a pair) =====================
+    // One thread issues everything: the tensor pipe runs one thread's MMAs back to back at 64 cycles each,
+    // but drops to ~87 cycles when two threads' MMAs interleave (tools/cg2_rate.cu). A tcgen05.mma blocks
+    // its thread once ~4 are queued (tools/mma_queue.cu), so whatever the thread does between two groups
+    // of MMAs has to fit under ~256 cycles of queued work or the pipe drains.
+    // The whole warp runs the loop converged; the MMAs and commits themselves go out from one elected lane.
+    if (rank == 0) {
       // per-Q-tile operands as scalars (x is a run-time value for the two PS issuers)
       auto tS_of = [&](int x) { return tmem_base + (uint32_t)x * 128u; };
       auto tO_of = [&](int x) { return tmem_base + 256u + (uint32_t)x * 128u; };
@@ -332,10 +339,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       auto q_desc_of = [&](int x) { return make_desc_kmajor_sw128(base + S::kQOff + (uint32_t)x * S::kTileBytes); };
       auto p_desc_of = [&](int x) { return make_desc_kmajor_sw128(base + S::kPOff + (uint32_t)x * S::kPBytes); };
       auto commit = [&](uint32_t bar) {
-        if (CG == 2) tc_commit_cg2(bar, 0b11);  // the same barrier in both CTAs of the pair
-        else tc_commit(bar);
+        if (CG == 2) tc_commit_cg2_elect(bar, 0b11);  // the same barrier in both CTAs of the pair
+        else tc_commit_elect(bar);
       };
-      auto issue_qk = [&](int x, uint32_t k_smem) {
+      // `probe` runs after the 4th and 6th MMA of a group -- with the queue full, i.e. for free
+      auto issue_qk = [&](int x, uint32_t k_smem, auto&& probe) {
         const uint64_t k_desc = make_desc_kmajor_sw128(k_smem);
         const uint64_t q_desc = q_desc_of(x);
         const uint32_t tS = tS_of(x);
@@ -344,10 +352,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint64_t off = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
           // a CTA of a pair holds kKvTile / 2 keys per head-dim panel
           const uint64_t koff = (uint64_t)(((ks / 4) * (kKvTile / CG * 128) + (ks % 4) * 32) >> 4);
-          umma_ss<kKind, CG>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
+          umma_ss<kKind, CG, true>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
+          if (ks == 3 || ks == 5) probe();
         }
       };
-      auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate) {
+      auto no_probe = [] {};
+      auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate, auto&& probe) {
         const uint64_t v_desc = make_desc_mnmajor_sw128(v_smem, kKvTile * 128, 1024);
         const uint64_t p_desc = p_desc_of(x);
         const uint32_t tS = tS_of(x), tO = tO_of(x);
@@ -359,10 +369,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
           if (PS) {
             const uint64_t poff = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
-            umma_ss<kKind, CG>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
+            umma_ss<kKind, CG, true>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
           } else {
-            umma_ts<kKind>(tO, tS + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
+            umma_ts<kKind, true>(tO, tS + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
           }
+          if (ks == (kKvTile / kKeysPerPV) / 2 - 1 || ks == (kKvTile / kKeysPerPV) * 3 / 4 - 1) probe();
         }
       };
       auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kKvBytes; };
@@ -370,7 +381,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(kv_full(u % S::kStages), (u / S::kStages) & 1u);
         tc_fence_after();
       };
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+      const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
 
       int j = next_active(0);
       if (j < p.n_kv_tiles) {
@@ -380,46 +391,105 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (PS) {
           // P travels through shared memory, so S_X is free again as soon as the softmax warps hold it in
           // registers: QK_X(t+1) is issued ahead of PV_X(t) and the only per-tile dependency chain left is
-          // the softmax itself. Ring items (order of first use): K(0) | K(t+1), V(t) | ...; each issuer
-          // releases a stage on its own, the stage's empty barrier counts both.
-          const int x = warp - 9;
-          const int role = 2 + x;
-          issue_qk(x, stage_addr(0));
-          commit(s_full(x));
-          commit(kv_empty(0));
-          uint32_t t = 0, u = 1;
-          while (true) {
-            const int jn = next_active(j + 1);
-            const bool has_next = jn < p.n_kv_tiles;
-            const uint32_t uK = u, uV = has_next ? u + 1 : u;
-            const uint32_t ph = t & 1u;
-            if (has_next) {
-              wait_full(uK);
-              mbar_wait(s_free(x), ph);
-              tc_fence_after();
-              trace_ev(p, tr, role, 0, t);
-              issue_qk(x, stage_addr(uK));
-              commit(s_full(x));
-              commit(kv_empty(uK % S::kStages));
-              trace_ev(p, tr, role, 1, t);
+          // the softmax itself. Per active tile t the groups go QK_A(t+1), PV_A(t), QK_B(t+1), PV_B(t); ring
+          // items (order of first use): K(0) | K(t+1), V(t) | ... While a group is being issued the barriers
+          // of the NEXT group are probed without blocking; only if they have not completed by the end of the
+          // group does the thread fall back to a blocking wait (a real dependency stall).
+          auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
+          auto ring_next = [&](uint32_t& st, uint32_t& par) {
+            if (++st == (uint32_t)S::kStages) {
+              st = 0;
+              par ^= 1u;
             }
-            wait_full(uV);
-            mbar_wait(p_ready(x), ph);
+          };
+          issue_qk(0, stage_smem(0), no_probe);
+          commit(s_full(0));
+          issue_qk(1, stage_smem(0), no_probe);
+          commit(s_full(1));
+          commit(kv_empty(0));
+          uint32_t st = 1u % S::kStages, par = 0u;  // ring cursor: item 1 = K(1) (or V(0) if there is no tile 1)
+          uint32_t t = 0;
+          bool ok = false;  // "the barriers of the group about to be issued were seen complete by a probe"
+          int jn = next_active(j + 1);
+          while (true) {
+            const bool has_next = jn < p.n_kv_tiles;
+            const int jn2 = has_next ? next_active(jn + 1) : jn;
+            const bool has_next2 = has_next && jn2 < p.n_kv_tiles;
+            const uint32_t ph = t & 1u;
+            const uint32_t sK = st, pK = par;  // K(t+1), if any
+            uint32_t sV = st, pV = par;        // V(t)
+            if (has_next) ring_next(sV, pV);
+            uint32_t sK2 = sV, pK2 = pV;       // K(t+2), if any
+            ring_next(sK2, pK2);
+            // ---- QK_A(t+1): K(t+1) landed, S_A(t) in registers ----
+            if (has_next) {
+              trace_ev(p, tr, 2, 4, t);
+              if (!ok) {
+                mbar_wait(kv_full(sK), pK);
+                trace_ev(p, tr, 2, 5, t);
+                mbar_wait(s_free(0), ph);
+              }
+              tc_fence_after();
+              trace_ev(p, tr, 2, 6, t);
+              ok = false;
+              trace_ev(p, tr, 2, 0, t);
+              issue_qk(0, stage_smem(sK), [&] { if (!ok) ok = mbar_test_wait(kv_full(sV), pV) && mbar_test_wait(p_ready(0), ph); });
+              commit(s_full(0));
+              trace_ev(p, tr, 2, 1, t);
+            } else {
+              ok = false;
+            }
+            // ---- PV_A(t): V(t) landed, P_A(t) written ----
+            if (!ok) {
+              mbar_wait(kv_full(sV), pV);
+              mbar_wait(p_ready(0), ph);
+            }
             tc_fence_after();
-            trace_ev(p, tr, role, 2, t);
-            issue_pv(x, stage_addr(uV), t != 0);
-            commit(o_done(x));
-            commit(kv_empty(uV % S::kStages));
-            trace_ev(p, tr, role, 3, t);
+            ok = false;
+            trace_ev(p, tr, 2, 2, t);
+            if (has_next) {
+              issue_pv(0, stage_smem(sV), t != 0, [&] { if (!ok) ok = mbar_test_wait(s_free(1), ph); });
+            } else {
+              issue_pv(0, stage_smem(sV), t != 0, [&] { if (!ok) ok = mbar_test_wait(p_ready(1), ph); });
+            }
+            commit(o_done(0));
+            trace_ev(p, tr, 2, 3, t);
+            // ---- QK_B(t+1) ----
+            if (has_next) {
+              if (!ok) mbar_wait(s_free(1), ph);
+              tc_fence_after();
+              ok = false;
+              trace_ev(p, tr, 3, 0, t);
+              issue_qk(1, stage_smem(sK), [&] { if (!ok) ok = mbar_test_wait(p_ready(1), ph); });
+              commit(s_full(1));
+              commit(kv_empty(sK));
+              trace_ev(p, tr, 3, 1, t);
+            }
+            // ---- PV_B(t) ----
+            if (!ok) mbar_wait(p_ready(1), ph);
+            tc_fence_after();
+            ok = false;
+            trace_ev(p, tr, 3, 2, t);
+            if (has_next2) {
+              issue_pv(1, stage_smem(sV), t != 0,
+                       [&] { if (!ok) ok = mbar_test_wait(kv_full(sK2), pK2) && mbar_test_wait(s_free(0), ph ^ 1u); });
+            } else {
+              issue_pv(1, stage_smem(sV), t != 0, no_probe);
+            }
+            commit(o_done(1));
+            commit(kv_empty(sV));
+            trace_ev(p, tr, 3, 3, t);
             if (!has_next) break;
-            u += 2;
+            st = sK2;
+            par = pK2;
             j = jn;
+            jn = jn2;
             ++t;
           }
         } else {
-        issue_qk(0, stage_addr(0));
+        issue_qk(0, stage_addr(0), no_probe);
         commit(s_full(0));
-        issue_qk(1, stage_addr(0));
+        issue_qk(1, stage_addr(0), no_probe);
         commit(s_full(1));
         commit(kv_empty(0));
         uint32_t t = 0;
@@ -438,23 +508,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(p_ready(0), ph);
           trace_ev(p, tr, 2, 1, t);
           tc_fence_after();
-          issue_pv(0, stage_addr(uV), t != 0);
+          issue_pv(0, stage_addr(uV), t != 0, no_probe);
           trace_ev(p, tr, 2, 4, t);
           commit(o_done(0));
           if (has_next) {
             trace_ev(p, tr, 2, 5, t);
-            issue_qk(0, stage_addr(uKn));
+            issue_qk(0, stage_addr(uKn), no_probe);
             commit(s_full(0));
           }
           trace_ev(p, tr, 2, 2, t);
           mbar_wait(p_ready(1), ph);
           trace_ev(p, tr, 2, 3, t);
           tc_fence_after();
-          issue_pv(1, stage_addr(uV), t != 0);
+          issue_pv(1, stage_addr(uV), t != 0, no_probe);
           commit(o_done(1));
           commit(kv_empty(uV % S::kStages));
           if (!has_next) break;
-          issue_qk(1, stage_addr(uKn));
+          issue_qk(1, stage_addr(uKn), no_probe);
           commit(s_full(1));
           commit(kv_empty(uKn % S::kStages));
           j = jn;
@@ -486,7 +556,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     uint32_t t = 0;
     for (int j = 0; j < p.n_kv_tiles; ++j) {
       if (!tile_active(j)) continue;
-      const bool tr = p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+      const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
       trace_ev(p, tr, x, 0, t);
       mbar_wait(s_full(x), t & 1u);
       trace_ev(p, tr, x, 1, t);
@@ -629,7 +699,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_arrive(p_ready(x));
       }
       trace_ev(p, tr, x, 5, t);
-      if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < kTraceTiles)
+      if (TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < kTraceTiles)
         atomicMax((unsigned long long*)&p.trace[(x * 8 + 6) * kTraceTiles + t], (unsigned long long)clock64());
       ++t;
     }
@@ -675,14 +745,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int HD, int DT, int EMU, bool PS, int CG>
-static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE>
+static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const AttnParams& p, cudaStream_t st) {
   using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2, PS, CG>;
   static bool attr_set[64] = {};
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
-  auto kern = attn_fwd_kernel<HD, DT, EMU, PS, CG>;
+  auto kern = attn_fwd_kernel<HD, DT, EMU, PS, CG, MASKED, TRACE>;
   if (!attr_set[dev]) {
     FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set[dev] = true;
@@ -705,8 +775,21 @@ static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return FDM_OK;
 }
 
-// experiment knobs: FDM_ATTN_PSMEM=0 keeps P in TMEM (aliasing S) instead of staging it through shared
-// memory; FDM_ATTN_CG=1 runs single CTAs instead of CTA pairs (hd 128, 16-bit operands)
+template <int HD, int DT, int EMU, bool PS, int CG>
+static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const AttnParams& p, cudaStream_t st) {
+  if (p.trace != nullptr) {
+    // the timeline build exists for the default dense bf16 hd-128 configurations only
+    if constexpr (HD == 128 && DT == kDtBF16 && EMU == 4) {
+      if (p.mask == nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, false, true>(tq, tk, tv, p, st);
+    }
+  }
+  return p.mask != nullptr ? launch_attn_k<HD, DT, EMU, PS, CG, true, false>(tq, tk, tv, p, st)
+                           : launch_attn_k<HD, DT, EMU, PS, CG, false, false>(tq, tk, tv, p, st);
+}
+
+// experiment knob: FDM_ATTN_CG=1 runs single CTAs (P in TMEM over S) instead of CTA pairs (P through shared
+// memory) for hd 128 with 16-bit operands
 static int attn_env(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -720,19 +803,13 @@ static bool attn_pair_setting() {
 static bool attn_use_pair(int64_t Sq, int64_t Sk) {
   return attn_pair_setting() && Sk >= 8 * kKvTile && Sq > 2 * kQTile;
 }
-static bool attn_psmem_setting() {
-  static int v = attn_env("FDM_ATTN_PSMEM", 0);
-  return v != 0;
-}
-
 template <int HD, int DT, int EMU>
 static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const AttnParams& p, cudaStream_t st) {
   if constexpr (HD == 128 && DT != kDtE4M3) {
     if (attn_use_pair(p.Sq, p.Sk)) return launch_attn_p<HD, DT, EMU, true, 2>(tq, tk, tv, p, st);
   }
-  return attn_psmem_setting() ? launch_attn_p<HD, DT, EMU, true, 1>(tq, tk, tv, p, st)
-                              : launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st);
+  return launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st);
 }
 
 // how many of every 32 exponentials run on the FMA pipe instead of MUFU (tuning knob; the default is
@@ -753,9 +830,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   const int emu = attn_emu_setting(HD);
   if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st);
   if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st);
-  if (emu <= 8) return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st);
-  if (emu <= 12) return launch_attn_e<HD, DT, 12>(tq, tk, tv, p, st);
-  return launch_attn_e<HD, DT, 16>(tq, tk, tv, p, st);
+  return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st);
 }
 
 static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,

@@ -82,6 +82,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking: has the phase with this parity completed? (acquire on success, like try_wait)
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
@@ -245,6 +259,22 @@ __device__ __forceinline__ void tc_commit_cg2(uint32_t bar, uint16_t mask) {
       : "memory");
 }
 
+// the same two, called from a fully converged warp: one elected lane commits
+__device__ __forceinline__ void tc_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}\n" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2_elect(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;\n}\n" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle:
 //   rows are 128 bytes, 8-row groups are 1024 bytes apart (SBO), LBO unused (=1).
 __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t saddr) {
@@ -282,66 +312,68 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t a_fmt, uint32_t b_fmt
 
 enum class MmaKind { F16, F8F6F4, I8 };
 
-// D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA (pair)
-template <MmaKind KIND, int CG = 1>
+// D[tmem] (+)= A[smem] * B[smem]; one thread issues on behalf of the CTA (pair).
+// ELECT = false: the calling thread issues (call it from one lane only).
+// ELECT = true : call it from a fully converged warp; one elected lane issues. All operands are then
+//                warp-uniform, which lets ptxas keep the descriptors in uniform registers and step them
+//                with uniform adds instead of moving them over (R2UR) before every MMA.
+#define FDM_UMMA_SS_ASM(CGS, KINDS)                                                                  \
+  if constexpr (ELECT) {                                                                             \
+    asm volatile("{\n.reg .pred p, e;\nelect.sync _|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"          \
+                 "@e tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], %1, %2, %3, p;\n}\n" ::"r"( \
+                     tmem_d),                                                                        \
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                                 \
+                 : "memory");                                                                        \
+  } else {                                                                                           \
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"                                         \
+                 "tcgen05.mma.cta_group::" CGS ".kind::" KINDS " [%0], %1, %2, %3, p;\n}\n" ::"r"(    \
+                     tmem_d),                                                                        \
+                 "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)                                 \
+                 : "memory");                                                                        \
+  }
+template <MmaKind KIND, int CG = 1, bool ELECT = false>
 __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                         uint32_t idesc, uint32_t accumulate) {
   if constexpr (KIND == MmaKind::F8F6F4 && CG == 1) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_SS_ASM("1", "f8f6f4")
   } else if constexpr (KIND == MmaKind::I8 && CG == 1) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_SS_ASM("1", "i8")
   } else if constexpr (KIND == MmaKind::F16 && CG == 1) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_SS_ASM("1", "f16")
   } else if constexpr (KIND == MmaKind::F8F6F4 && CG == 2) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_SS_ASM("2", "f8f6f4")
   } else if constexpr (KIND == MmaKind::I8 && CG == 2) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_SS_ASM("2", "i8")
   } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_SS_ASM("2", "f16")
   }
 }
+#undef FDM_UMMA_SS_ASM
 // D[tmem] (+)= A[tmem] * B[smem]
-template <MmaKind KIND>
+#define FDM_UMMA_TS_ASM(KINDS)                                                                      \
+  if constexpr (ELECT) {                                                                            \
+    asm volatile("{\n.reg .pred p, e;\nelect.sync _|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n"         \
+                 "@e tcgen05.mma.cta_group::1.kind::" KINDS " [%0], [%1], %2, %3, p;\n}\n" ::"r"(    \
+                     tmem_d),                                                                       \
+                 "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)                               \
+                 : "memory");                                                                       \
+  } else {                                                                                          \
+    asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"                                        \
+                 "tcgen05.mma.cta_group::1.kind::" KINDS " [%0], [%1], %2, %3, p;\n}\n" ::"r"(       \
+                     tmem_d),                                                                       \
+                 "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)                               \
+                 : "memory");                                                                       \
+  }
+template <MmaKind KIND, bool ELECT = false>
 __device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
                                         uint32_t idesc, uint32_t accumulate) {
   if constexpr (KIND == MmaKind::F16) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_TS_ASM("f16")
   } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    FDM_UMMA_TS_ASM("f8f6f4")
   }
 }
+#undef FDM_UMMA_TS_ASM
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive 32-bit columns
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

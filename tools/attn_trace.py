@@ -26,8 +26,10 @@ for t in range(8, 20):
             f" | softB waitS {bb[0]:6d} Srdy {bb[1]:6d} ld {bb[2]-bb[1]:4d} max {bb[3]-bb[2]:4d} exp {bb[4]-bb[3]:4d} st+arr {bb[5]-bb[4]:4d} -> {bb[5]:6d}")
     if pair:
         for r, nm in ((2, "mmaA"), (3, "mmaB")):
-            m = [int(tr[r, e, t]) - t0 for e in range(4)]
-            line += f" | {nm} qk_go {m[0]:6d} +{m[1]-m[0]:4d} pv_go {m[2]:6d} +{m[3]-m[2]:4d}"
+            m = [int(tr[r, e, t]) - t0 for e in range(7)]
+            if r == 2:
+                line += f" | top {m[4]:6d} probed={int(tr[2, 7, t])} Kfull +{m[5]-m[4]:4d} sfree +{m[6]-m[5]:4d}"
+            line += f" | {nm} qk_go {m[0]:6d} issue +{m[1]-m[0]:4d} gap +{m[2]-m[1]:4d} pv_issue +{m[3]-m[2]:4d} -> {m[3]:6d}"
     else:
         m = [int(tr[2, e, t]) - t0 for e in range(6)]
         line += f" | MMA Vrdy {m[0]:6d} P_A {m[1]:6d} pv_issued +{m[4]-m[1]:4d} qk_issued +{m[2]-m[1]:4d} P_B {m[3]:6d}"
