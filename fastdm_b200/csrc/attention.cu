@@ -561,6 +561,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(s_full(x), t & 1u);
       trace_ev(p, tr, x, 1, t);
       tc_fence_after();
+      // PS: has PV_X(t-1) finished reading the P tile? Probed here, needed only at the first store of P
+      bool p_free = !PS || t == 0;
+      if (PS && t > 0) p_free = mbar_test_wait(o_done(x), (t - 1) & 1u);
       const int valid = p.Sk - j * kKvTile;  // keys of this tile inside the sequence
       bool seg0 = true, seg1 = true;
       if (has_mask) {
@@ -604,6 +607,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const float mx = fmaxf(fmax3(max32(s0), max32(s1), max32(s2)), max32(s3));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool need = m_new > m_run + kRescaleThreshold;  // first finite max always triggers
+      bool tmem_dirty = false;
       if (__any_sync(0xffffffffu, need)) {
         const float m_next = need ? m_new : m_run;
         const float alpha = (m_run == -INFINITY) ? 0.f : ex2(m_run - m_next);
@@ -611,6 +615,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         m_run = m_next;
         if (t > 0) {
           // O_X may only be touched between PV_X(t-1) and PV_X(t)
+          tmem_dirty = true;
           mbar_wait(o_done(x), (t - 1) & 1u);
           tc_fence_after();
 #pragma unroll
@@ -626,7 +631,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       trace_ev(p, tr, x, 3, t);
       // the shared-memory P tile is read by PV_X(t-1) until o_done(x) completes its phase
-      if (PS && t > 0) mbar_wait(o_done(x), (t - 1) & 1u);
+      if (PS && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
       // ---- P = exp2(S*scale - m): over the first columns of S_X in TMEM, or into the P tile in smem ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
@@ -690,7 +695,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       trace_ev(p, tr, x, 4, t);
       if (PS) fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core's reads
-      tmem_st_wait();
+      if (!PS || tmem_dirty) tmem_st_wait();  // P in TMEM, or O rescaled through TMEM
       tc_fence_before();
       if (CG == 2) {
         __syncwarp();
