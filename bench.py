@@ -194,7 +194,8 @@ def workload_config(wl, n):
                     parallelism=f"ulysses-sp{n}" if n > 1 else "single-gpu", l2="per-step activations (>=0.8 GB each) exceed the 126 MB L2; no flush")
     return dict(workload="FLUX.1-dev full transformer forward, 1024x2048 (8192 image + 512 text tokens, 19 double + 38 single "
                          "blocks, d=3072, 24x128 heads), FP8 per-token x per-channel W8A8, bf16 attention, random-init weights",
-                parallelism="single-gpu" if n == 1 else f"replicas x{n}", l2="per-step activations (0.14 GB each) exceed the 126 MB L2; no flush")
+                parallelism="single-gpu" if n == 1 else f"replicas x{n}", l2="per-step activations (0.14 GB each) exceed the 126 MB L2; no flush",
+                launch="whole step replayed as one CUDA graph (fastdm_b200.graph.GraphedStep); --no-graph launches eagerly")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -314,7 +315,7 @@ def attention_roofline(wl, world, device, pk):
     ach = flops / ms / 1e9
     # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
     # (profiles/r01_ncu_full_summary.txt): only the N=1 launch shapes were captured.
-    traffic = {("wan", 1): 4.494e9, ("flux", 1): 1.939e8}.get((wl, world))
+    traffic = {("wan", 1): 4.403e9, ("flux", 1): 1.927e8}.get((wl, world))
     return dict(bound="tensor", kernel="attn_fwd_kernel<128,bf16>", achieved=ach, peak=pk["bf16"], unit="TFLOP/s",
                 frac=ach / pk["bf16"], traffic=traffic, traffic_unit="bytes/launch (dram read+write, ncu --set full)",
                 algorithmic_bytes=4.0 * S * H * hd * 2, ms_per_launch=ms, flops_per_launch=flops,
@@ -332,6 +333,7 @@ def main():
     ap.add_argument("--cpu-tokens", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flux", action="store_true", help="skip the secondary FLUX numbers at N=1")
+    ap.add_argument("--no-graph", action="store_true", help="launch the FLUX step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -375,6 +377,9 @@ def main():
         fn = fn0
     dev_inputs = to_device(host, device)
     torch.cuda.synchronize()
+    if wl == "flux" and not args.no_graph:
+        from fastdm_b200.graph import GraphedStep
+        fn = GraphedStep(fn, dev_inputs)   # ~1300 launches per step: replayed as one CUDA graph
 
     with ClockSampler(local_rank) as clocks:
         c0 = _lib.launch_count
@@ -397,6 +402,9 @@ def main():
         torch.cuda.empty_cache()
         fmodel, fhost = build_flux(device, FLUX["double"], FLUX["single"])
         ffn = step_fn("flux", fmodel, None)
+        if not args.no_graph:
+            from fastdm_b200.graph import GraphedStep
+            ffn = GraphedStep(ffn, to_device(fhost, device))
         fms = timed_steps(ffn, to_device(fhost, device), 10, 3, 1, device)
         fe2e, fh2d, fd2h = timed_e2e(ffn, fhost, 5, 1, device)
         froof = attention_roofline("flux", 1, device, pk)

@@ -83,6 +83,12 @@ def last_error() -> str:
 launch_count = 0
 
 
+def add_launches(n: int):
+    """CUDA-graph replays launch the captured kernels without passing through check()."""
+    global launch_count
+    launch_count += n
+
+
 def check(rc: int, what: str):
     global launch_count
     launch_count += 1
