@@ -27,10 +27,63 @@ from . import ops
 from .layers import FeedForward, QLinear, Quantized, load_linear, quantize
 
 
-def _mod(scale: torch.Tensor, shift: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+class ModChunk:
+    """One AdaLN modulation vector [B, dim] whose two fp32 forms were prepared for all blocks at once by
+    `AdaLNTable` (one GEMM + two elementwise kernels per step instead of ~20 tiny launches per block):
+    `one_plus` = (1 + x) evaluated in the model dtype, widened to fp32; `f32` = x widened to fp32."""
+
+    __slots__ = ("one_plus", "f32")
+
+    def __init__(self, one_plus: torch.Tensor, f32: torch.Tensor):
+        self.one_plus, self.f32 = one_plus, f32
+
+
+def _f32(x) -> torch.Tensor:
+    return x.f32 if isinstance(x, ModChunk) else x.float().contiguous()
+
+
+def _mod(scale, shift) -> Tuple[torch.Tensor, torch.Tensor]:
     """(1 + scale) evaluated in the tensor dtype as the reference does (normalization.py:196), then
     widened to fp32 for the fused kernel (exact)."""
+    if isinstance(scale, ModChunk):
+        return scale.one_plus, shift.f32
     return (1 + scale).float().contiguous(), shift.float().contiguous()
+
+
+class AdaLNTable:
+    """All AdaLN-Zero modulation linears of a model that share one conditioning vector (FLUX: norm1.linear,
+    norm1_context.linear of every double block, norm.linear of every single block -- flux.py:288, 99), stacked
+    into one [sum N_i, K] weight so that a step computes every block's modulation with ONE GEMM
+    (the weights are read once either way: 6.4 GB for FLUX.1-dev). The blocks' own QLinear objects are
+    re-pointed at views of the stacked storage, so nothing is duplicated and `block.forward(temb)` without a
+    table keeps working."""
+
+    def __init__(self, linears):
+        self.offsets = []
+        ws, bs, off = [], [], 0
+        for lin in linears:
+            n = lin.weight.shape[1]
+            self.offsets.append((off, n))
+            ws.append(lin.weight.t())
+            bs.append(lin.bias)
+            off += n
+        self.weight_store = torch.cat(ws, dim=0).contiguous()          # [sum N, K]
+        self.bias = torch.cat(bs, dim=0).contiguous()
+        for lin, (o, n) in zip(linears, self.offsets):
+            lin.weight = self.weight_store[o:o + n].t()
+            lin.bias = self.bias[o:o + n]
+
+    def compute(self, cond: torch.Tensor):
+        """cond = silu(temb) [B, K] -> (one_plus, f32), both fp32 [B, sum N]."""
+        e = torch.addmm(self.bias, cond, self.weight_store.t())
+        return (1 + e).float(), e.float()
+
+    def chunks(self, tables, index: int, n_chunks: int):
+        one_plus, f32 = tables
+        o, n = self.offsets[index]
+        d = n // n_chunks
+        mk = (lambda t, a: t[:, a:a + d]) if one_plus.shape[0] == 1 else (lambda t, a: t[:, a:a + d].contiguous())
+        return tuple(ModChunk(mk(one_plus, o + k * d), mk(f32, o + k * d)) for k in range(n_chunks))
 
 
 class _JointDiTBlock:
@@ -100,9 +153,9 @@ class _JointDiTBlock:
 
         new_hidden = torch.empty_like(hidden_states)
         new_encoder = None if context_pre_only else torch.empty_like(encoder_hidden_states)
-        g_msa, g_mlp = gate_msa.float().contiguous(), gate_mlp.float().contiguous()
+        g_msa, g_mlp = _f32(gate_msa), _f32(gate_mlp)
         if not context_pre_only:
-            cg_msa, cg_mlp = c_gate_msa.float().contiguous(), c_gate_mlp.float().contiguous()
+            cg_msa, cg_mlp = _f32(c_gate_msa), _f32(c_gate_mlp)
         for b in range(B):
             # hidden = hidden + gate_msa * to_out(attn)      (flux.py:153-154, qwenimage.py:98-99)
             aq = quantize(attn[b, S_txt:], qt)
@@ -146,7 +199,11 @@ class FluxTransformerBlock(_JointDiTBlock):
         self.norm1_context_linear = load_linear(sd, [f"{p}.norm1_context.linear"], None, dv)
         self._load_common(sd, p, q, dv, "ff", "ff_context")
 
-    def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None):
+    def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None,
+                mod=None):
+        """`mod` = (img chunks, txt chunks) prepared by an AdaLNTable; without it the block computes its own."""
+        if mod is not None:
+            return self._forward_joint(hidden_states, encoder_hidden_states, mod[0], mod[1], image_rotary_emb)
         # AdaLN parameters (M = batch GEMMs, unquantized as in the reference)
         emb = self.norm1_linear.forward(F.silu(temb))
         cemb = self.norm1_context_linear.forward(F.silu(temb))
@@ -232,11 +289,14 @@ class FluxSingleTransformerBlock:
         self.norm_k_weight = sd[f"{p}.attn.norm_k.weight"].to(dv).contiguous()
         self.scale = self.hd ** -0.5
 
-    def forward(self, hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None):
+    def forward(self, hidden_states, temb, image_rotary_emb=None, joint_attention_kwargs=None, mod=None):
         B, S, d = hidden_states.shape
         H, hd, qt = self.heads, self.hd, self.quant_type
-        emb = self.norm_linear.forward(F.silu(temb))
-        shift_msa, scale_msa, gate = emb.chunk(3, dim=1)
+        if mod is not None:   # (shift, scale, gate) prepared by an AdaLNTable
+            shift_msa, scale_msa, gate = mod
+        else:
+            emb = self.norm_linear.forward(F.silu(temb))
+            shift_msa, scale_msa, gate = emb.chunk(3, dim=1)
         hid2 = hidden_states.reshape(B * S, d)
         a, c = _mod(scale_msa, shift_msa)
         # one quantised copy of norm_hidden_states feeds both proj_mlp and qkv (flux.py:60-67)
@@ -253,7 +313,7 @@ class FluxSingleTransformerBlock:
         cq = quantize(cat2, qt)
         out = torch.empty_like(hidden_states)
         # hidden = residual + gate * proj_out(cat)      (flux.py:70-72)
-        self.proj_out.forward(cq, gate=gate.float().contiguous(), residual=hid2, rows_per_batch=S,
+        self.proj_out.forward(cq, gate=_f32(gate), residual=hid2, rows_per_batch=S,
                               out=out.view(B * S, d))
         return out
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .blocks import FluxSingleTransformerBlock, FluxTransformerBlock, WanTransformerBlock
+from .blocks import AdaLNTable, FluxSingleTransformerBlock, FluxTransformerBlock, WanTransformerBlock
 from .layers import QLinear, load_linear
 
 
@@ -173,6 +173,10 @@ class FluxTransformer2DModelCore:
             p = f"single_transformer_blocks.{i}"
             self.single_transformer_blocks.append(FluxSingleTransformerBlock(
                 part(lambda: random_flux_single_sd(p, d, self.hd, g, device)), p, self.heads, self.hd, quant_dtype, device))
+        # every block's AdaLN modulation comes from the same silu(temb): one stacked GEMM per step
+        self.use_adaln_table = True
+        self.adaln = AdaLNTable([l for b in self.transformer_blocks for l in (b.norm1_linear, b.norm1_context_linear)]
+                                + [b.norm_linear for b in self.single_transformer_blocks])
 
     def forward(self, hidden_states, encoder_hidden_states, pooled_projections, timestep, img_ids, txt_ids,
                 guidance=None):
@@ -192,12 +196,17 @@ class FluxTransformer2DModelCore:
         if img_ids.ndim == 3:
             img_ids = img_ids[0]
         rope = flux_rope_table(torch.cat((txt_ids, img_ids), dim=0), self.axes_dims_rope, dt)    # flux.py:417-428
-        for block in self.transformer_blocks:                                                    # flux.py:445-452
-            encoder_hidden_states, hidden_states = block.forward(hidden_states, encoder_hidden_states, temb, rope)
+        use_table = self.use_adaln_table
+        tables = self.adaln.compute(F.silu(temb)) if use_table else None
+        for i, block in enumerate(self.transformer_blocks):                                      # flux.py:445-452
+            mod = (self.adaln.chunks(tables, 2 * i, 6), self.adaln.chunks(tables, 2 * i + 1, 6)) if use_table else None
+            encoder_hidden_states, hidden_states = block.forward(hidden_states, encoder_hidden_states, temb, rope, mod=mod)
         t = encoder_hidden_states.shape[1]
         hidden_states = torch.cat([encoder_hidden_states, hidden_states], dim=1)                 # flux.py:466
-        for block in self.single_transformer_blocks:                                             # flux.py:468-474
-            hidden_states = block.forward(hidden_states, temb, rope)
+        n_double = 2 * len(self.transformer_blocks)
+        for i, block in enumerate(self.single_transformer_blocks):                               # flux.py:468-474
+            hidden_states = block.forward(hidden_states, temb, rope,
+                                          mod=self.adaln.chunks(tables, n_double + i, 3) if use_table else None)
         hidden_states = hidden_states[:, t:, ...]
         # AdaLayerNormContinuous (normalization.py:90-128) + proj_out
         emb = self.norm_out_linear.forward(F.silu(temb).to(dt))

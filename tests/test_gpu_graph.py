@@ -33,3 +33,22 @@ def test_graphed_flux_step_matches_eager():
         torch.cuda.synchronize()
         assert _lib.launch_count - c0 == graphed.launches_per_replay
         assert torch.equal(got, want)
+
+
+def test_flux_adaln_table_matches_per_block_modulation():
+    """One stacked modulation GEMM per step (AdaLNTable) vs each block running its own small linear."""
+    from fastdm_b200.models import FluxTransformer2DModelCore
+
+    dev, bf = "cuda", torch.bfloat16
+    model = FluxTransformer2DModelCore(num_layers=2, num_single_layers=3, device=dev, seed=11)
+    g = torch.Generator().manual_seed(7)
+    n_img, n_txt = 512, 64
+    args = (torch.rand(1, n_img, 64, generator=g).to(bf).to(dev), torch.rand(1, n_txt, 4096, generator=g).to(bf).to(dev),
+            torch.rand(1, 768, generator=g).to(bf).to(dev), torch.tensor([0.4]).to(bf).to(dev),
+            torch.zeros(n_img, 3, device=dev), torch.zeros(n_txt, 3, device=dev), torch.tensor([3.5]).to(bf).to(dev))
+    y_table = model.forward(*args)[0].float()
+    model.use_adaln_table = False
+    y_block = model.forward(*args)[0].float()
+    cos = torch.nn.functional.cosine_similarity(y_table.flatten(), y_block.flatten(), dim=0).item()
+    assert cos > 0.9999, cos
+    assert (y_table - y_block).abs().max().item() <= 0.02 * y_block.abs().max().item()
