@@ -237,8 +237,8 @@ def test_final_latent_cosine_after_n_steps(quant):
     """north_star: "a final-latent cosine after N steps is also reported". An 8-step flow-matching Euler loop
     x <- x + dt * v(x, t) whose velocity model is a FLUX double + single block pair (random init, the step's
     timestep embedding changes every step) runs once on the product path (CUDA, C ABI) and once on the oracle
-    (CPU); quantisation error compounds over the steps, so this bounds its drift. Measured on B200: fp8 0.9996,
-    int8 0.9999 (printed with -s)."""
+    (CPU); quantisation error compounds over the steps, so this bounds its drift. Measured on B200: fp8 0.999999,
+    int8 1.000000 (printed with -s)."""
     from fastdm_b200.blocks import FluxSingleTransformerBlock, FluxTransformerBlock
     from oracle import blocks_ref as B
 
