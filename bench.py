@@ -333,6 +333,7 @@ def main():
     ap.add_argument("--cpu-tokens", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flux", action="store_true", help="skip the secondary FLUX numbers at N=1")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the radial-sparse Wan variant at N=1")
     ap.add_argument("--no-graph", action="store_true", help="launch the FLUX step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
@@ -397,6 +398,20 @@ def main():
         extra["ms_per_step_comm_stubbed"] = ms_stub
     roof = attention_roofline(wl, world, device, pk)
 
+    if rank == 0 and wl == "wan" and world == 1 and not args.no_sparse and not args.layers:
+        # BASELINE configs[4] "dense vs Sparge sparse attention": the same step with the reference's radial block
+        # mask (examples/sparse/radial_attn_wan.json: block 64, decay 0.3, first layer dense) on self-attention
+        from fastdm_b200.sparse import radial_block_mask, sparge_mask_convert
+        tpf = (WAN["height"] // 2) * (WAN["width"] // 2)
+        m64 = radial_block_mask(WAN["frames"], tpf, 64, 0.3, "wan", device=device)
+        conv = sparge_mask_convert(m64, 64)                                   # [S/128, S/64]
+        smask = conv.to(torch.int8)[None, None].expand(1, WAN["heads"], -1, -1).contiguous()
+        sfn = lambda d: model.forward(d["latent"], d["timestep"], d["prompt"], sparse_mask=smask, dense_layers=1)[0]  # noqa: E731
+        sms = timed_steps(sfn, dev_inputs, max(1, min(args.steps, 3)), 3, 1, device)
+        extra["wan_sparse"] = dict(ms_per_step=sms, mask="radial (fastdm/sparse/xsparse.py), block 64, decay_factor 0.3, "
+                                   "dense_layers 1, all steps sparse", block_sparsity=1.0 - conv.float().mean().item(),
+                                   speedup_vs_dense=ms / sms)
+        del smask, m64, conv
     if rank == 0 and wl == "wan" and world == 1 and not args.no_flux and not args.layers:
         del model
         torch.cuda.empty_cache()

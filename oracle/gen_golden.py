@@ -345,6 +345,23 @@ def main():
         save(f"block_wan_{tag}.pt", dict(dim=dim, heads=heads, hd=hd, ffn=ffn, x=x, enc=enc, temb=temb6, cos=cos,
                                          sin=sin, sd=sd, y=y))
 
+    # ---- radial block masks (fastdm/sparse/xsparse.py:71-185, 238-260): the policy FastDM hands to sdpa_sparse
+    from fastdm.sparse.config import RadialAttnConfig
+    from fastdm.sparse.xsparse import RadialAttn, sparge_mask_convert as ref_convert
+    from fastdm_b200.sparse import radial_block_mask, sparge_mask_convert
+    cases = []
+    for (frames, tpf, bs, decay) in ((6, 300, 64, 0.3), (5, 384, 128, 0.5), (9, 256, 64, 0.3), (16, 480, 64, 0.3)):
+        ra = RadialAttn(RadialAttnConfig(sparse_algorithm="radial", block_size=bs, decay_factor=decay, model_type="wan"))
+        ra.post_init(video_token_num=frames * tpf, num_frame=frames)
+        s = frames * tpf // bs * bs
+        RadialAttn._log_mask = None
+        m = ra.gen_log_mask_shrinked(s, "cpu")
+        conv = ref_convert(m, bs, "sm100") if m.shape[0] % 2 == 0 else None
+        mine = radial_block_mask(frames, tpf, bs, decay, "wan", total_tokens=s)
+        ok &= torch.equal(m, mine) and (conv is None or torch.equal(conv, sparge_mask_convert(mine, bs)))
+        cases.append(dict(frames=frames, tpf=tpf, block=bs, decay=decay, mask=m, converted=conv))
+    save("radial_mask.pt", cases)
+
     print("restatement reproduces every fixture:", ok)
     if not ok:
         sys.exit(1)
