@@ -356,6 +356,8 @@ def main():
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG set on the box) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     wl = "wan" if args.workload == "auto" else args.workload
     if wl == "flux" and world > 1:
