@@ -113,11 +113,14 @@ class _JointDiTBlock:
         self.scale = self.hd ** -0.5
 
     def _forward_joint(self, hidden_states, encoder_hidden_states, img_mod, txt_mod, image_rotary_emb,
-                       dual_mod=None, context_pre_only=False, eps1=None):
+                       dual_mod=None, context_pre_only=False, eps1=None, ulysses=None, rope_pos=None):
         """img_mod / txt_mod: (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), each [B, dim].
         SD3.5 extras: `dual_mod` = (shift_msa2, scale_msa2, gate_msa2) runs the image-only second attention
         (self.attn2_*); `context_pre_only` (last block): txt_mod = (shift, scale), the text stream only feeds
-        k/v and is dropped afterwards; `eps1` overrides the first LayerNorm's eps."""
+        k/v and is dropped afterwards; `eps1` overrides the first LayerNorm's eps.
+        Ulysses (Qwen-Image): hidden_states / encoder_hidden_states are this rank's token shards of the two
+        streams, `rope_pos` = (first text row, first image row) of the shards in `image_rotary_emb`; the joint
+        attention runs head-sharded over the full [text | image] sequence through `ulysses.attention`."""
         B, S_img, d = hidden_states.shape
         S_txt = encoder_hidden_states.shape[1]
         S = S_txt + S_img
@@ -145,11 +148,15 @@ class _JointDiTBlock:
         for b in range(B):
             self.add_qkv_proj.forward(cq.rows(b * S_txt, (b + 1) * S_txt), out=qkv[b, :S_txt])
             self.qkv.forward(xq.rows(b * S_img, (b + 1) * S_img), out=qkv[b, S_txt:])
+            pos_txt, pos_img = (0, S_txt) if rope_pos is None else rope_pos
             ops.qk_norm_rope_(qkv[b, :S_txt], self.norm_added_q_weight, self.norm_added_k_weight, image_rotary_emb,
-                              H, H, hd, 0, d, 0, self.eps)
+                              H, H, hd, 0, d, pos_txt, self.eps)
             ops.qk_norm_rope_(qkv[b, S_txt:], self.norm_q_weight, self.norm_k_weight, image_rotary_emb,
-                              H, H, hd, 0, d, S_txt, self.eps)
-        attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale)
+                              H, H, hd, 0, d, pos_img, self.eps)
+        if ulysses is not None and ulysses.P > 1:
+            attn = ulysses.attention(qkv, self.scale)      # keys of every rank's shards, this rank's queries
+        else:
+            attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale)
 
         new_hidden = torch.empty_like(hidden_states)
         new_encoder = None if context_pre_only else torch.empty_like(encoder_hidden_states)
@@ -228,10 +235,14 @@ class QwenImageTransformerBlock(_JointDiTBlock):
         self._load_common(sd, p, q, dv, "img_mlp", "txt_mlp")
 
     def forward(self, hidden_states, encoder_hidden_states, encoder_hidden_states_mask, temb, image_rotary_emb=None,
-                joint_attention_kwargs=None):
-        img = self.img_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)   # mod1 = (shift, scale, gate), mod2 likewise
-        txt = self.txt_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)
-        return self._forward_joint(hidden_states, encoder_hidden_states, img, txt, image_rotary_emb)
+                joint_attention_kwargs=None, mod=None, ulysses=None, rope_pos=None):
+        if mod is not None:    # (img chunks, txt chunks) prepared by an AdaLNTable
+            img, txt = mod
+        else:
+            img = self.img_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)   # mod1 = (shift, scale, gate), mod2 likewise
+            txt = self.txt_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)
+        return self._forward_joint(hidden_states, encoder_hidden_states, img, txt, image_rotary_emb,
+                                   ulysses=ulysses, rope_pos=rope_pos)
 
 
 class JointTransformerBlock(_JointDiTBlock):

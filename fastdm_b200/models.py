@@ -17,7 +17,8 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .blocks import AdaLNTable, FluxSingleTransformerBlock, FluxTransformerBlock, WanTransformerBlock
+from .blocks import (AdaLNTable, FluxSingleTransformerBlock, FluxTransformerBlock, QwenImageTransformerBlock,
+                     WanTransformerBlock)
 from .layers import QLinear, load_linear
 
 
@@ -307,3 +308,113 @@ class WanTransformer3DModelCore:
         if ulysses is not None and ulysses.P > 1:
             y = ulysses.gather_tokens(y, dim=1)
         return (self.unpatchify(y, grid, batch),)
+
+
+# ---- Qwen-Image ------------------------------------------------------------------------------------
+def qwen_rope_table(frame, height, width, txt_len, axes_dim=(16, 56, 56), theta=10000.0, dtype=torch.bfloat16,
+                    device="cuda"):
+    """QwenEmbedRope.forward with scale_rope=True (fastdm/layer/embeddings.py:762-857) + the merge of
+    qwenimage.py:309-313: rows [text | image], each [cos(hd/2) | sin(hd/2)]. Image rows: frame index, then height
+    and width positions centred on zero; text rows: one position max(h//2, w//2) + i on all three axes."""
+    def angles(pos, dim):
+        inv = 1.0 / torch.pow(torch.tensor(theta), torch.arange(0, dim, 2, dtype=torch.float32) / dim)
+        return torch.outer(pos.to(torch.float32), inv)
+
+    centred = lambda n: torch.cat([torch.arange(-(n - n // 2), 0), torch.arange(0, n // 2)])  # noqa: E731
+    f = angles(torch.arange(frame), axes_dim[0]).view(frame, 1, 1, -1).expand(frame, height, width, -1)
+    hh = angles(centred(height), axes_dim[1]).view(1, height, 1, -1).expand(frame, height, width, -1)
+    ww = angles(centred(width), axes_dim[2]).view(1, 1, width, -1).expand(frame, height, width, -1)
+    img = torch.cat([f, hh, ww], dim=-1).reshape(frame * height * width, -1)
+    tpos = max(height // 2, width // 2) + torch.arange(txt_len)
+    txt = torch.cat([angles(tpos, a) for a in axes_dim], dim=-1)
+    ang = torch.cat([txt, img], dim=0)
+    return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1).to(dtype).to(device).contiguous()
+
+
+def random_qwen_block_sd(prefix, dim, head_dim, g, device):
+    sd, p = {}, prefix
+    _rand_linear(sd, f"{p}.img_mod.1", 6 * dim, dim, g, device)
+    _rand_linear(sd, f"{p}.txt_mod.1", 6 * dim, dim, g, device)
+    for n in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0", "to_add_out"):
+        _rand_linear(sd, f"{p}.attn.{n}", dim, dim, g, device)
+    for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        sd[f"{p}.attn.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g, device=device)).to(torch.bfloat16)
+    for ff in ("img_mlp", "txt_mlp"):
+        _rand_linear(sd, f"{p}.{ff}.net.0.proj", 4 * dim, dim, g, device)
+        _rand_linear(sd, f"{p}.{ff}.net.2", dim, 4 * dim, g, device)
+    return sd
+
+
+class QwenImageTransformer2DModelCore:
+    """fastdm/model/qwenimage.py:126-352 (60 MMDiT blocks, d = 3072, 24 x 128 heads, INT8 W8A8 by default in
+    the reference). `ulysses`: sequence parallelism -- the image and the text tokens are each sharded over the
+    ranks, every block's joint attention is head-sharded (two all-to-alls), everything else is token-local;
+    every rank receives the same inputs and returns the same full output."""
+
+    def __init__(self, num_layers=60, attention_head_dim=128, num_attention_heads=24, in_channels=64, out_channels=64,
+                 joint_attention_dim=3584, patch_size=2, axes_dims_rope=(16, 56, 56), quant_dtype=torch.int8,
+                 device="cuda", seed=0, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.inner_dim = d = self.heads * self.hd
+        self.axes_dims_rope = axes_dims_rope
+        self.device = device
+        g = torch.Generator(device=device).manual_seed(seed)
+        sd = state_dict
+
+        def part(make):
+            return sd if sd is not None else make()
+
+        def pre():
+            s = {}
+            _rand_linear(s, "time_text_embed.timestep_embedder.linear_1", d, 256, g, device)
+            _rand_linear(s, "time_text_embed.timestep_embedder.linear_2", d, d, g, device)
+            s["txt_norm.weight"] = (1 + 0.1 * torch.randn(joint_attention_dim, generator=g, device=device)).to(torch.bfloat16)
+            _rand_linear(s, "img_in", d, in_channels, g, device)
+            _rand_linear(s, "txt_in", d, joint_attention_dim, g, device)
+            _rand_linear(s, "norm_out.linear", 2 * d, d, g, device)
+            _rand_linear(s, "proj_out", out_channels, d, g, device)   # patch_size^2 * (out_channels / patch_size^2)
+            return s
+
+        s = part(pre)
+        self.timestep_embedder = _MLP(s, "time_text_embed.timestep_embedder", "silu", device)
+        self.txt_norm_weight = s["txt_norm.weight"].to(device).contiguous()
+        self.img_in = load_linear(s, ["img_in"], None, device)
+        self.txt_in = load_linear(s, ["txt_in"], None, device)
+        self.norm_out_linear = load_linear(s, ["norm_out.linear"], None, device)
+        self.proj_out = load_linear(s, ["proj_out"], None, device)
+        self.transformer_blocks: List[QwenImageTransformerBlock] = []
+        for i in range(num_layers):
+            p = f"transformer_blocks.{i}"
+            self.transformer_blocks.append(QwenImageTransformerBlock(
+                part(lambda: random_qwen_block_sd(p, d, self.hd, g, device)), p, self.heads, self.hd, quant_dtype, device))
+        self.use_adaln_table = True
+        self.adaln = AdaLNTable([l for b in self.transformer_blocks for l in (b.img_mod_proj, b.txt_mod_proj)])
+
+    def forward(self, hidden_states, encoder_hidden_states, timestep, img_shape, ulysses=None):
+        """hidden_states [1, f*h*w, in_channels] (packed latents), encoder_hidden_states [1, T, joint_dim],
+        img_shape = (f, h, w) of the packed latent grid."""
+        dt = hidden_states.dtype
+        x = self.img_in.forward(hidden_states)                                                    # qwenimage.py:286
+        enc = ops.rms_norm(encoder_hidden_states.reshape(-1, encoder_hidden_states.shape[-1]).contiguous(),
+                           self.txt_norm_weight, 1e-6).view_as(encoder_hidden_states)             # :289
+        enc = self.txt_in.forward(enc)                                                            # :290
+        temb = self.timestep_embedder.forward(
+            get_timestep_embedding(timestep.to(dt), 256, flip_sin_to_cos=True, downscale_freq_shift=0, scale=1000).to(dt))
+        T = enc.shape[1]
+        rope = qwen_rope_table(*img_shape, T, self.axes_dims_rope, dtype=dt, device=x.device)
+        rope_pos = None
+        if ulysses is not None and ulysses.P > 1:
+            x = ulysses.shard_tokens(x, dim=1)
+            enc = ulysses.shard_tokens(enc, dim=1)
+            rope_pos = (ulysses.rank * enc.shape[1], T + ulysses.rank * x.shape[1])
+        tables = self.adaln.compute(F.silu(temb)) if self.use_adaln_table else None
+        for i, block in enumerate(self.transformer_blocks):                                       # :331-340
+            mod = (self.adaln.chunks(tables, 2 * i, 6), self.adaln.chunks(tables, 2 * i + 1, 6)) if tables is not None else None
+            enc, x = block.forward(x, enc, None, temb, rope, mod=mod, ulysses=ulysses, rope_pos=rope_pos)
+        emb = self.norm_out_linear.forward(F.silu(temb).to(dt))                                   # AdaLayerNormContinuous
+        scale, shift = torch.chunk(emb, 2, dim=1)
+        x = F.layer_norm(x, (self.inner_dim,), None, None, 1e-6) * (1 + scale)[:, None, :] + shift[:, None, :]
+        y = self.proj_out.forward(x)
+        if ulysses is not None and ulysses.P > 1:
+            y = ulysses.gather_tokens(y, dim=1)
+        return (y,)

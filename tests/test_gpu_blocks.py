@@ -272,3 +272,31 @@ def test_final_latent_cosine_after_n_steps(quant):
     cos = float((a @ b) / (a.norm() * b.norm()))
     print(f"final-latent cosine after {steps} steps ({quant}): {cos:.6f}")
     assert cos >= 0.999, cos
+
+
+def test_qwen_image_model_forward_and_rope_table():
+    """Whole Qwen-Image core (2 layers): runs, is finite, AdaLN table == per-block modulation; the rope table
+    follows QwenEmbedRope (scale_rope): text rows sit at max(h//2, w//2) + i on all axes, image rows are centred."""
+    from fastdm_b200.models import QwenImageTransformer2DModelCore, qwen_rope_table
+
+    dev, bf = "cuda", torch.bfloat16
+    tab = qwen_rope_table(1, 4, 6, 5, dtype=torch.float32, device="cpu")
+    assert tab.shape == (5 + 24, 128)
+    # text row i: the same position on all three axes -> cos of the first frequency (1.0) of each axis block agrees
+    pos = max(4 // 2, 6 // 2) + torch.arange(5).float()
+    assert torch.allclose(tab[:5, 0], torch.cos(pos)) and torch.allclose(tab[:5, 8], torch.cos(pos)) and torch.allclose(tab[:5, 36], torch.cos(pos))
+    # image row (f=0, h=0, w=0): height position -(4 - 2) = -2, width position -(6 - 3) = -3
+    assert torch.allclose(tab[5, 8], torch.cos(torch.tensor(-2.0))) and torch.allclose(tab[5, 64 + 36], torch.sin(torch.tensor(-3.0)))
+    model = QwenImageTransformer2DModelCore(num_layers=2, attention_head_dim=128, num_attention_heads=2,
+                                            joint_attention_dim=256, quant_dtype=torch.int8, device=dev, seed=5)
+    g = torch.Generator().manual_seed(2)
+    f, h, w, T = 1, 16, 20, 77
+    lat = torch.randn(1, f * h * w, 64, generator=g).to(bf).to(dev)
+    txt = torch.randn(1, T, 256, generator=g).to(bf).to(dev)
+    ts = torch.tensor([0.3]).to(dev)
+    y = model.forward(lat, txt, ts, (f, h, w))[0].float()
+    assert y.shape == (1, f * h * w, 64) and bool(torch.isfinite(y).all())
+    model.use_adaln_table = False
+    y2 = model.forward(lat, txt, ts, (f, h, w))[0].float()
+    cos = torch.nn.functional.cosine_similarity(y.flatten(), y2.flatten(), dim=0).item()
+    assert cos > 0.9999, cos

@@ -81,3 +81,53 @@ def test_wan_block_ulysses_2gpu_equals_single_gpu(lib, tmp_path):
     for overlap, (err, cos) in res.items():
         # identical arithmetic per head; only the GEMM column-group split changes nothing numerically
         assert cos >= 0.9999 and err <= 0.05, f"overlap={overlap}: err {err}, cos {cos}"
+
+
+QWEN_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["FDM_ROOT"])
+from fastdm_b200.models import QwenImageTransformer2DModelCore
+from fastdm_b200.ulysses import UlyssesAttention
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+dev, bf = "cuda", torch.bfloat16
+heads, hd = 4, 128
+res = {}
+for quant in (torch.int8, torch.float8_e4m3fn):
+    model = QwenImageTransformer2DModelCore(num_layers=2, attention_head_dim=hd, num_attention_heads=heads,
+                                            joint_attention_dim=256, quant_dtype=quant, device=dev, seed=3)
+    g = torch.Generator().manual_seed(1)
+    f, h, w, T = 1, 16, 24, 96            # 384 image tokens + 96 text tokens: both divisible by 2 ranks
+    lat = torch.randn(1, f * h * w, 64, generator=g).to(bf).to(dev)
+    txt = torch.randn(1, T, 256, generator=g).to(bf).to(dev)
+    ts = torch.tensor([0.6]).to(dev)
+    ref = model.forward(lat, txt, ts, (f, h, w))[0]
+    uly = UlyssesAttention(heads, hd)
+    out = model.forward(lat, txt, ts, (f, h, w), ulysses=uly)[0]
+    torch.cuda.synchronize()
+    err = (out.float() - ref.float()).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(out.flatten().double(), ref.flatten().double(), dim=0).item()
+    res[str(quant)] = (err, cos, float(ref.float().abs().max()))
+if rank == 0:
+    print("QWEN_ULYSSES_RESULT", res)
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+@pytest.mark.timeout(600)
+def test_qwen_image_model_ulysses_2gpu_equals_single_gpu(lib, tmp_path):
+    """Qwen-Image (joint text + image attention, INT8 and FP8): tokens of both streams sharded over 2 ranks,
+    head-sharded joint attention through two all-to-alls == the single-GPU forward."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "qwen_worker.py"
+    script.write_text(QWEN_WORKER)
+    env = dict(os.environ, FDM_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29513", str(script)],
+                       capture_output=True, text=True, env=env, timeout=550)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("QWEN_ULYSSES_RESULT")][0]
+    res = eval(line.split("QWEN_ULYSSES_RESULT", 1)[1])
+    for quant, (err, cos, mag) in res.items():
+        assert cos >= 0.9999 and err <= 0.05 * mag, f"{quant}: err {err}, cos {cos}, |ref| {mag}"
