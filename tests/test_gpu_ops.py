@@ -403,6 +403,27 @@ def test_attention_vs_fp32_reference(ops, case):
     assert (y[:1, rows].cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
 
 
+@pytest.mark.parametrize("case", [(2, 1500, 2100, 3, 128, torch.bfloat16), (1, 1100, 1024, 2, 128, torch.float16),
+                                  (3, 513, 1300, 1, 128, torch.bfloat16), (1, 300, 1100, 2, 128, torch.bfloat16)])
+def test_attention_cta_pair_edge_shapes(ops, case):
+    """hd-128 shapes that take the CTA-pair kernel: batches, odd numbers of 256-row query blocks (the pair's
+    second CTA is partly or entirely beyond Sq), ragged last K/V tile, fp16; and one (Sq <= 512 rows but > 256)
+    with a single pair."""
+    b, sq, sk, h, hd, dt = case
+    g = torch.Generator(device=DEV).manual_seed(sq + sk)
+    q = torch.randn(b, sq, h * hd, device=DEV, generator=g).to(dt)
+    k = torch.randn(b, sk, h * hd, device=DEV, generator=g).to(dt)
+    v = torch.randn(b, sk, h * hd, device=DEV, generator=g).to(dt)
+    scale = 1.0 / hd ** 0.5
+    y = ops.scaled_dot_product_attention(q, k, v, h, h, hd, scale=scale)
+    qf = q.view(b, sq, h, hd).transpose(1, 2).float()
+    kf = k.view(b, sk, h, hd).transpose(1, 2).float()
+    vf = v.view(b, sk, h, hd).transpose(1, 2).float()
+    ref = torch.matmul(torch.softmax(torch.matmul(qf, kf.transpose(-1, -2)) * scale, dim=-1), vf).to(dt)
+    err = (y.view(b, sq, h, hd).transpose(1, 2).float() - ref.float()).abs().max().item()
+    assert err <= ATOL_ATTN, f"max abs err {err}"
+
+
 def test_attention_strided_views_of_fused_qkv(ops):
     # value is a last-dim slice of the fused qkv projection: layer/transformer.py:269,300
     torch.manual_seed(1)
