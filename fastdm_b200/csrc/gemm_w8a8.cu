@@ -35,9 +35,9 @@ struct GemmSmem {
   static constexpr int kBBytes = BN * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = kStages * kStageBytes;
-  // epilogue per-column parameters: scale_b, bias, azp_adj
+  // epilogue per-column parameters: scale_b, bias, azp_adj, gate
   static constexpr int kEpiOff = kRing;
-  static constexpr int kEpiBytes = 3 * BN * 4;
+  static constexpr int kEpiBytes = 4 * BN * 4;
   static constexpr int kBarOff = kEpiOff + kEpiBytes;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // + alignment slack
@@ -88,6 +88,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   float* s_sb = reinterpret_cast<float*>(smem + S::kEpiOff);
   float* s_bias = s_sb + BN;
   int32_t* s_adj = reinterpret_cast<int32_t*>(s_bias + BN);
+  float* s_gate = reinterpret_cast<float*>(s_adj + BN);
   const uint32_t bar_base = base + S::kBarOff;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S::kStages + s); };
@@ -212,6 +213,9 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         s_bias[i] = b;
         if (INT8) s_adj[i] = (ok && p.azp_adj != nullptr) ? p.azp_adj[col] : 0;
+        // the gate row of the tile's batch, staged once per tile: read per element from global it was two thirds
+        // of the epilogue's load instructions (ncu: 313 k load requests against 98 k stores, lg_throttle stalls)
+        if (p.gate != nullptr) s_gate[i] = ok ? p.gate[(int64_t)(m0 / p.rows_per_batch) * p.N + col] : 1.f;
       }
       named_bar_sync(1, kEpiThreads);
 
@@ -280,6 +284,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (p.gate != nullptr || p.residual != nullptr) {
             // reference chains (flux.py:153-154,161-163,69-72; wan.py:97,105,112): the linear's output
             // is a T tensor, then gate * out (+ rounding for bf16 tensor ops), then residual + .
+            // rows of one tile normally share a batch (and with it the staged gate row)
+            const bool gate_staged = (m0 / p.rows_per_batch) == (min(m0 + kBM, p.M) - 1) / p.rows_per_batch;
             const float* grow = p.gate ? p.gate + (int64_t)(row / p.rows_per_batch) * p.N + col0 : nullptr;
             const bool has_res = p.residual != nullptr;
 #pragma unroll
@@ -291,7 +297,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   gq[j] = 1.f;
                   rq[j] = 0.f;
                 }
-                if (grow) {
+                if (grow && gate_staged) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) gq[j] = s_gate[c * 32 + q * 8 + j];
+                } else if (grow) {
                   const float4 g0 = *reinterpret_cast<const float4*>(grow + q * 8);
                   const float4 g1 = *reinterpret_cast<const float4*>(grow + q * 8 + 4);
                   gq[0] = g0.x; gq[1] = g0.y; gq[2] = g0.z; gq[3] = g0.w;
