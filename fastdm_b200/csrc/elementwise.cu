@@ -559,7 +559,12 @@ __global__ void __launch_bounds__(256) rope_kernel(T* __restrict__ q, T* __restr
     T* base = (h < q_heads) ? (q + b * qbs + s * qts + (int64_t)h * head_size)
                             : (k + b * kbs + s * kts + (int64_t)(h - q_heads) * head_size);
     const T* row = cs + s * cs_stride;
-    if (!NEOX) {
+    if (!NEOX && Elem<T>::kId == FDM_BF16) {
+      const U128 raw = ldg128(base + v * 8);
+      uint32_t xp[4] = {raw.x, raw.y, raw.z, raw.w};
+      rope4_bf16(xp, *reinterpret_cast<const uint2*>(row + v * 4), *reinterpret_cast<const uint2*>(row + half + v * 4));
+      stg128(base + v * 8, U128{xp[0], xp[1], xp[2], xp[3]});
+    } else if (!NEOX) {
       // elements 8v..8v+7 -> pairs 4v..4v+3
       float x[8];
       unpack8<T>(ldg128(base + v * 8), x);
@@ -676,11 +681,19 @@ __global__ void __launch_bounds__(256) qk_norm_rope_head_kernel(
   const int rows = (int)tokens * heads;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int warp_count = gridDim.x * (blockDim.x >> 5);
+  constexpr bool kBf = Elem<T>::kId == FDM_BF16;
   float wqv[8], wkv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) wqv[j] = wkv[j] = 1.f;
-  if (wq) unpack8<T>(ldg128(wq + li * 8), wqv);
-  if (wk) unpack8<T>(ldg128(wk + li * 8), wkv);
+  U128 wq_raw = {0, 0, 0, 0}, wk_raw = {0, 0, 0, 0};
+  if (wq) {
+    wq_raw = ldg128(wq + li * 8);
+    unpack8<T>(wq_raw, wqv);
+  }
+  if (wk) {
+    wk_raw = ldg128(wk + li * 8);
+    unpack8<T>(wk_raw, wkv);
+  }
   const float inv_cols = 1.0f / (float)head_size;
   const int half = head_size >> 1;
   constexpr int UNROLL = 4;
@@ -710,14 +723,27 @@ __global__ void __launch_bounds__(256) qk_norm_rope_head_kernel(
 #pragma unroll
       for (int j = 0; j < 8; ++j) ss += f[j] * f[j];
       ss = warp_sum<LANES>(ss);
-      if (do_norm) {
-        const float rs = rsqrtf(ss * inv_cols + eps);
+      if constexpr (kBf) {
+        // packed bf16 path (see bmul2): same bits as the element-wise chain below
+        uint32_t xp[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        if (do_norm) norm_scale8_bf16(f, rsqrtf(ss * inv_cols + eps), isk[u] ? wk_raw : wq_raw, xp);
+        if (ok[u]) {
+          if (cs != nullptr) {
+            const T* crow = cs + (pos0 + tok[u]) * cs_stride;
+            rope4_bf16(xp, *reinterpret_cast<const uint2*>(crow + li * 4), *reinterpret_cast<const uint2*>(crow + half + li * 4));
+          }
+          stg128(ptr[u], U128{xp[0], xp[1], xp[2], xp[3]});
+        }
+      } else {
+        if (do_norm) {
+          const float rs = rsqrtf(ss * inv_cols + eps);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = round_to<T>(round_to<T>(f[j] * rs) * (isk[u] ? wkv[j] : wqv[j]));
-      }
-      if (ok[u]) {
-        if (cs != nullptr) rope8<T>(f, cs + (pos0 + tok[u]) * cs_stride, li * 8, half);
-        stg128(ptr[u], pack8<T>(f));
+          for (int j = 0; j < 8; ++j) f[j] = round_to<T>(round_to<T>(f[j] * rs) * (isk[u] ? wkv[j] : wqv[j]));
+        }
+        if (ok[u]) {
+          if (cs != nullptr) rope8<T>(f, cs + (pos0 + tok[u]) * cs_stride, li * 8, half);
+          stg128(ptr[u], pack8<T>(f));
+        }
       }
     }
   }
@@ -760,14 +786,25 @@ __global__ void __launch_bounds__(512) qk_norm_rope_row_kernel(
     if (v < nvec) {
       float f[8];
       unpack8<T>(raw[i], f);
-      if (w != nullptr) {
-        float wv[8];
-        unpack8<T>(ldg128(w + (int64_t)v * 8), wv);
+      if constexpr (Elem<T>::kId == FDM_BF16) {
+        uint32_t xp[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+        if (w != nullptr) norm_scale8_bf16(f, rs, ldg128(w + (int64_t)v * 8), xp);
+        if (cs != nullptr) {
+          const T* crow = cs + (pos0 + tok) * cs_stride;
+          const int col = (v * 8) % head_size;
+          rope4_bf16(xp, *reinterpret_cast<const uint2*>(crow + (col >> 1)), *reinterpret_cast<const uint2*>(crow + half + (col >> 1)));
+        }
+        stg128(row + (int64_t)v * 8, U128{xp[0], xp[1], xp[2], xp[3]});
+      } else {
+        if (w != nullptr) {
+          float wv[8];
+          unpack8<T>(ldg128(w + (int64_t)v * 8), wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = round_to<T>(round_to<T>(f[j] * rs) * wv[j]);
+          for (int j = 0; j < 8; ++j) f[j] = round_to<T>(round_to<T>(f[j] * rs) * wv[j]);
+        }
+        if (cs != nullptr) rope8<T>(f, cs + (pos0 + tok) * cs_stride, (v * 8) % head_size, half);
+        stg128(row + (int64_t)v * 8, pack8<T>(f));
       }
-      if (cs != nullptr) rope8<T>(f, cs + (pos0 + tok) * cs_stride, (v * 8) % head_size, half);
-      stg128(row + (int64_t)v * 8, pack8<T>(f));
     }
   }
 }
