@@ -920,22 +920,48 @@ __global__ void __launch_bounds__(512) ln_mod_quant_kernel(
         const float4 c1 = __ldg(reinterpret_cast<const float4*>(Cr + v * 8 + 4));
         c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
       }
+      bool packed_done = false;
+      if constexpr (ROUND_STEPS && Elem<T>::kId == FDM_BF16) {
+        // T(T(T(n) * A) + C) with A, C themselves bf16 values (they are "evaluated in the tensor dtype",
+        // normalization.py:196) is three native packed bf16 operations; checked per vector, any other A / C
+        // takes the element-wise fp32 path below
+        uint32_t lowbits = 0u;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float n = (f[j] - mean) * rstd;
-        if (ROUND_STEPS) {
-          n = round_to<T>(n);
-          if (Ar) n = round_to<T>(__fmul_rn(n, a[j]));
-          if (Cr) n = __fadd_rn(n, c[j]);
-        } else {
-          if (Ar) n = __fmul_rn(n, a[j]);
-          if (Cr) n = __fadd_rn(n, c[j]);
+        for (int j = 0; j < 8; ++j) lowbits |= __float_as_uint(a[j]) | __float_as_uint(c[j]);
+        if (Ar && Cr && (lowbits & 0xffffu) == 0u) {
+          uint32_t y[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t n2 = pack_bf16((f[2 * q] - mean) * rstd, (f[2 * q + 1] - mean) * rstd);
+            const uint32_t a2 = (__float_as_uint(a[2 * q]) >> 16) | (__float_as_uint(a[2 * q + 1]) & 0xffff0000u);
+            const uint32_t c2 = (__float_as_uint(c[2 * q]) >> 16) | (__float_as_uint(c[2 * q + 1]) & 0xffff0000u);
+            y[q] = badd2(bmul2(n2, a2), c2);
+            const float lo = bf16lo(y[q]), hi = bf16hi(y[q]);
+            mn = fminf(mn, fminf(lo, hi));
+            mx = fmaxf(mx, fmaxf(lo, hi));
+          }
+          raw[i] = U128{y[0], y[1], y[2], y[3]};
+          packed_done = true;
         }
-        f[j] = round_to<T>(n);
-        mn = fminf(mn, f[j]);
-        mx = fmaxf(mx, f[j]);
       }
-      raw[i] = pack8<T>(f);
+      if (!packed_done) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float n = (f[j] - mean) * rstd;
+          if (ROUND_STEPS) {
+            n = round_to<T>(n);
+            if (Ar) n = round_to<T>(__fmul_rn(n, a[j]));
+            if (Cr) n = __fadd_rn(n, c[j]);
+          } else {
+            if (Ar) n = __fmul_rn(n, a[j]);
+            if (Cr) n = __fadd_rn(n, c[j]);
+          }
+          f[j] = round_to<T>(n);
+          mn = fminf(mn, f[j]);
+          mx = fmaxf(mx, f[j]);
+        }
+        raw[i] = pack8<T>(f);
+      }
       if (y_out) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
     }
   }

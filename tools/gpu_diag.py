@@ -245,8 +245,8 @@ def block_kernels_perf():
 
     for (M, K) in ((8704, 3072), (8704, 15360), (80640, 5120)):
         nbuf = max(2, int(400e6 // (M * K * 2)) + 1)
-        a = torch.rand(1, K, device=DEV) + 0.5
-        c = torch.rand(1, K, device=DEV)
+        a = (torch.rand(1, K, device=DEV) + 0.5).to(BF).float()   # bf16-valued, as the AdaLN chain produces them
+        c = torch.rand(1, K, device=DEV).to(BF).float()
         ms = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF),
                       lambda x: ops.layernorm_modulate_quant(x, a, c, M, torch.float8_e4m3fn), nbuf)
         gb = (3 * M * K + 4 * M) / ms / 1e6
