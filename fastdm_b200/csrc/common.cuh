@@ -203,6 +203,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * phi;
 }
 
+// 32-byte global accesses (sm_100: LDG/STG.E.ENL2.256): two 16-byte vectors at a 32-byte aligned address. One
+// instruction covers a whole 32-byte sector per lane -- half the LSU requests of two 16-byte accesses, and stores
+// never write partial sectors.
+__device__ __forceinline__ void ldg256(const void* p, U128& lo, U128& hi) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w), "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const U128& lo, const U128& hi) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w),
+               "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w)
+               : "memory");
+}
+
 // ---- packed bf16 arithmetic --------------------------------------------------------------------------------
 // The reference's bf16 tensor ops are "fp32 op, round to bf16". For two bf16 operands that is exactly what the
 // native packed instructions compute: a product of two 8-bit significands is exact in fp32, so RN_bf16(fp32

@@ -57,6 +57,7 @@ struct GemmParams {
   int act;
   int tiles_m, tiles_n;
   int vec_store;
+  int vec32;  // rows of d (and of the residual) are 32-byte aligned: 256-bit loads / stores
   // fused residual epilogue: d = residual + gate[row / rows_per_batch, n] * T(linear)
   const float* gate;     // fp32 [batches, N] or NULL
   const void* residual;  // out_dtype [M, N] (row stride ldr) or NULL; may alias d
@@ -235,9 +236,14 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int cc = 0; cc < kMyChunks; ++cc) {
           const int c = col_half * kMyChunks + cc;
+          if (p.vec32 && n0 + c * 32 + 32 <= p.N) {
+            ldg256(rrow + c * 32, resv[cc][0], resv[cc][1]);
+            ldg256(rrow + c * 32 + 16, resv[cc][2], resv[cc][3]);
+          } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (n0 + c * 32 + q * 8 < p.N) resv[cc][q] = ldg128(rrow + c * 32 + q * 8);
+            for (int q = 0; q < 4; ++q)
+              if (n0 + c * 32 + q * 8 < p.N) resv[cc][q] = ldg128(rrow + c * 32 + q * 8);
+          }
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -321,7 +327,26 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          if (p.vec_store) {
+          if (p.vec32 && col0 + 32 <= p.N) {
+            uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + col0;
+            U128 o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (bf) {
+                o[q].x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+                o[q].y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+                o[q].z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+                o[q].w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+              } else {
+                o[q].x = pack_f16(v[q * 8 + 0], v[q * 8 + 1]);
+                o[q].y = pack_f16(v[q * 8 + 2], v[q * 8 + 3]);
+                o[q].z = pack_f16(v[q * 8 + 4], v[q * 8 + 5]);
+                o[q].w = pack_f16(v[q * 8 + 6], v[q * 8 + 7]);
+              }
+            }
+            stg256(dst, o[0], o[1]);
+            stg256(dst + 16, o[2], o[3]);
+          } else if (p.vec_store) {
             uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + col0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -466,6 +491,8 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   p.tiles_m = (int)tiles_m;
   p.tiles_n = (int)tiles_n;
   p.vec_store = (ldd % 8 == 0 && (uintptr_t)d % 16 == 0) ? 1 : 0;
+  p.vec32 = (ldd % 16 == 0 && (uintptr_t)d % 32 == 0 &&
+             (residual == nullptr || (ldr % 16 == 0 && (uintptr_t)residual % 32 == 0))) ? 1 : 0;
   if (gate != nullptr || residual != nullptr) {
     FDM_REQUIRE(rows_per_batch > 0, "gemm: rows_per_batch must be positive");
     FDM_REQUIRE(gate == nullptr || (uintptr_t)gate % 16 == 0, "gemm: gate must be 16-byte aligned fp32");
