@@ -16,6 +16,8 @@
 //   fp8 : out = T( (acc*sA)*sB + bias )                                     (:33, torch._scaled_mm)
 //   int8: out = T( T( float(acc - azp*azp_adj) * (sA*sB) ) + bias )         (:67-74)
 // Reference CUDA path being replaced: csrc/torch_bindings.cpp:24-160 -> csrc/gemm/*.cu (CUTLASS).
+#include <stdlib.h>
+
 #include "sm100.cuh"
 
 namespace fdm {
@@ -455,6 +457,10 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   if (bn == 128 && tiles_m * ((N + 127) / 128) < sms) bn = 64;
   if (N <= 64) bn = 64;
   else if (N <= 128 && bn > 128) bn = 128;
+  if (const char* e = getenv("FDM_GEMM_BN")) {  // experiments only
+    const int v = atoi(e);
+    if (v == 64 || v == 128 || v == 256) bn = v;
+  }
   const int64_t tiles_n = (N + bn - 1) / bn;
   FDM_REQUIRE(tiles_m * tiles_n < (1LL << 31), "gemm: too many tiles");
 
