@@ -61,6 +61,7 @@ struct AttnSmem {
 struct AttnParams {
   void* o;
   int64_t o_bs, o_ts;
+  int o_vec32;
   const int8_t* mask;
   int B, H, Sq, Sk;
   int n_kv_tiles;
@@ -759,14 +760,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int i = 0; i < 32; ++i) r[i] = 0u;
       }
       if (row_ok) {
+        U128 o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          U128 o;
-          o.x = pack2<DT>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
-          o.y = pack2<DT>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
-          o.z = pack2<DT>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
-          o.w = pack2<DT>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
-          stg128(out_row + c * 32 + q * 8, o);
+          o[q].x = pack2<DT>(__uint_as_float(r[q * 8 + 0]) * inv, __uint_as_float(r[q * 8 + 1]) * inv);
+          o[q].y = pack2<DT>(__uint_as_float(r[q * 8 + 2]) * inv, __uint_as_float(r[q * 8 + 3]) * inv);
+          o[q].z = pack2<DT>(__uint_as_float(r[q * 8 + 4]) * inv, __uint_as_float(r[q * 8 + 5]) * inv);
+          o[q].w = pack2<DT>(__uint_as_float(r[q * 8 + 6]) * inv, __uint_as_float(r[q * 8 + 7]) * inv);
+        }
+        if (p.o_vec32) {  // 32-byte aligned rows: 256-bit stores (half the requests, whole sectors)
+          stg256(out_row + c * 32, o[0], o[1]);
+          stg256(out_row + c * 32 + 16, o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) stg128(out_row + c * 32 + q * 8, o[q]);
         }
       }
     }
@@ -932,6 +939,7 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   p.o = o;
   p.o_bs = o_bs;
   p.o_ts = o_ts;
+  p.o_vec32 = (o_ts % 16 == 0 && o_bs % 16 == 0 && (uintptr_t)o % 32 == 0 && (hd * 2) % 32 == 0) ? 1 : 0;
   p.mask = block_mask;
   p.B = (int)B;
   p.H = H;
