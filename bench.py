@@ -183,7 +183,7 @@ def run_reference(args, rank):
                 config=workload_config(wl, 1),
                 cpu_baseline=dict(value=v, unit="ms", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=v, unit="ms", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(wl, n):
@@ -322,7 +322,31 @@ def attention_roofline(wl, world, device, pk):
                 peak_source=pk["src"] + ", bf16 burst (kernel timed alone)")
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout. Libraries print there too (NCCL's version banner when NCCL_DEBUG is
+    set, torchrun warnings), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes to a
+    duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -451,7 +475,7 @@ def main():
                 e2e=dict(value=e2e_ms, unit="ms", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                 step_tflops_per_s=step_tflop * 1e3 / ms, **extra)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
