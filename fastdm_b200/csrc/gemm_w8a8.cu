@@ -39,7 +39,7 @@ struct GemmSmem {
   static constexpr int kRing = kStages * kStageBytes;
   // epilogue per-column parameters: scale_b, bias, azp_adj, gate
   static constexpr int kEpiOff = kRing;
-  static constexpr int kEpiBytes = 4 * BN * 4;
+  static constexpr int kEpiBytes = 4 * BN * 4 + BN * 2 + 16;  // ... + gate as bf16 + two "gate is not bf16" flags
   static constexpr int kBarOff = kEpiOff + kEpiBytes;
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // + alignment slack
@@ -92,6 +92,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   float* s_bias = s_sb + BN;
   int32_t* s_adj = reinterpret_cast<int32_t*>(s_bias + BN);
   float* s_gate = reinterpret_cast<float*>(s_adj + BN);
+  uint16_t* s_gate16 = reinterpret_cast<uint16_t*>(s_gate + BN);      // the same gate row as bf16 bit patterns
+  int* s_gate_inexact = reinterpret_cast<int*>(s_gate16 + BN);        // [2], indexed by tile parity
   const uint32_t bar_base = base + S::kBarOff;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (S::kStages + s); };
@@ -199,10 +201,12 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int row_in_tile = lane_group * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    int tile_par = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, tile_par ^= 1) {
       int tm, tn;
       tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
       const int m0 = tm * kBM, n0 = tn * BN;
+      if (epi_tid == 0) s_gate_inexact[tile_par] = 0;  // last read two tiles ago
       named_bar_sync(1, kEpiThreads);
       for (int i = epi_tid; i < BN; i += kEpiThreads) {
         const int col = n0 + i;
@@ -218,7 +222,12 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (INT8) s_adj[i] = (ok && p.azp_adj != nullptr) ? p.azp_adj[col] : 0;
         // the gate row of the tile's batch, staged once per tile: read per element from global it was two thirds
         // of the epilogue's load instructions (ncu: 313 k load requests against 98 k stores, lg_throttle stalls)
-        if (p.gate != nullptr) s_gate[i] = ok ? p.gate[(int64_t)(m0 / p.rows_per_batch) * p.N + col] : 1.f;
+        if (p.gate != nullptr) {
+          const float gv = ok ? p.gate[(int64_t)(m0 / p.rows_per_batch) * p.N + col] : 1.f;
+          s_gate[i] = gv;
+          s_gate16[i] = (uint16_t)(__float_as_uint(gv) >> 16);
+          if ((__float_as_uint(gv) & 0xffffu) != 0u) s_gate_inexact[tile_par] = 1;
+        }
       }
       named_bar_sync(1, kEpiThreads);
 
@@ -296,6 +305,32 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const bool gate_staged = (m0 / p.rows_per_batch) == (min(m0 + kBM, p.M) - 1) / p.rows_per_batch;
             const float* grow = p.gate ? p.gate + (int64_t)(row / p.rows_per_batch) * p.N + col0 : nullptr;
             const bool has_res = p.residual != nullptr;
+            // FLUX / Qwen / SD3.5 chain T(residual + T(gate * T(linear))) with a bf16-valued gate: three native
+            // packed bf16 operations per pair of columns (see common.cuh bmul2), the residual stays packed
+            const bool packed = bf && p.vec_store && p.round_steps && grow != nullptr && has_res && gate_staged &&
+                                s_gate_inexact[tile_par] == 0 && col0 + 32 <= p.N;
+            if (packed) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 g4 = *reinterpret_cast<const uint4*>(s_gate16 + c * 32 + q * 8);
+                const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w};
+                const uint32_t rw[4] = {resv[cc][q].x, resv[cc][q].y, resv[cc][q].z, resv[cc][q].w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int pr = 0; pr < 4; ++pr)
+                  ow[pr] = badd2(rw[pr], bmul2(pack_bf16(v[q * 8 + 2 * pr], v[q * 8 + 2 * pr + 1]), gw[pr]));
+                resv[cc][q] = U128{ow[0], ow[1], ow[2], ow[3]};
+              }
+              uint16_t* dst = reinterpret_cast<uint16_t*>(p.d) + (int64_t)row * p.ldd + col0;
+              if (p.vec32) {
+                stg256(dst, resv[cc][0], resv[cc][1]);
+                stg256(dst + 16, resv[cc][2], resv[cc][3]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) stg128(dst + q * 8, resv[cc][q]);
+              }
+              continue;  // next 32-column chunk
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               if (col0 + q * 8 < p.N) {

@@ -272,7 +272,7 @@ def block_kernels_perf():
         sb = torch.rand(N, 1, device=DEV)
         bias = torch.randn(N, device=DEV).to(BF)
         resid = torch.randn(M, N, device=DEV).to(BF)
-        gate = torch.randn(1, N, device=DEV)
+        gate = torch.randn(1, N, device=DEV).to(BF).float()   # bf16-valued, as the AdaLN chain produces it
         obuf = torch.empty(M, N, device=DEV, dtype=BF)
         fl = 2.0 * M * N * K
         t_plain = timeit(lambda: ops.fp8_matmul(a, b, sa, sb, BF, bias, out=obuf))
