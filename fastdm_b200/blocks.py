@@ -121,6 +121,7 @@ class _JointDiTBlock:
         Ulysses (Qwen-Image): hidden_states / encoder_hidden_states are this rank's token shards of the two
         streams, `rope_pos` = (first text row, first image row) of the shards in `image_rotary_emb`; the joint
         attention runs head-sharded over the full [text | image] sequence through `ulysses.attention`."""
+        hidden_states, encoder_hidden_states = hidden_states.contiguous(), encoder_hidden_states.contiguous()
         B, S_img, d = hidden_states.shape
         S_txt = encoder_hidden_states.shape[1]
         S = S_txt + S_img
@@ -158,8 +159,10 @@ class _JointDiTBlock:
         else:
             attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale)
 
-        new_hidden = torch.empty_like(hidden_states)
-        new_encoder = None if context_pre_only else torch.empty_like(encoder_hidden_states)
+        # (empty_like would inherit the strides of a transposed / sliced input)
+        new_hidden = torch.empty(hidden_states.shape, device=hidden_states.device, dtype=hidden_states.dtype)
+        new_encoder = None if context_pre_only else torch.empty(encoder_hidden_states.shape, device=hidden_states.device,
+                                                                dtype=encoder_hidden_states.dtype)
         g_msa, g_mlp = _f32(gate_msa), _f32(gate_mlp)
         if not context_pre_only:
             cg_msa, cg_mlp = _f32(c_gate_msa), _f32(c_gate_mlp)

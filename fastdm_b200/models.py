@@ -17,8 +17,8 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .blocks import (AdaLNTable, FluxSingleTransformerBlock, FluxTransformerBlock, QwenImageTransformerBlock,
-                     WanTransformerBlock)
+from .blocks import (AdaLNTable, FluxSingleTransformerBlock, FluxTransformerBlock, JointTransformerBlock,
+                     QwenImageTransformerBlock, WanTransformerBlock)
 from .layers import QLinear, load_linear
 
 
@@ -418,3 +418,97 @@ class QwenImageTransformer2DModelCore:
         if ulysses is not None and ulysses.P > 1:
             y = ulysses.gather_tokens(y, dim=1)
         return (y,)
+
+
+# ---- SD3 / SD3.5 -----------------------------------------------------------------------------------
+def random_sd3_block_sd(prefix, dim, head_dim, g, device, context_pre_only=False, use_dual_attention=False):
+    sd, p = {}, prefix
+    _rand_linear(sd, f"{p}.norm1.linear", (9 if use_dual_attention else 6) * dim, dim, g, device)
+    _rand_linear(sd, f"{p}.norm1_context.linear", (2 if context_pre_only else 6) * dim, dim, g, device)
+    names = ["to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_out.0"] + ([] if context_pre_only else ["to_add_out"])
+    for n in names:
+        _rand_linear(sd, f"{p}.attn.{n}", dim, dim, g, device)
+    for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        sd[f"{p}.attn.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g, device=device)).to(torch.bfloat16)
+    if use_dual_attention:
+        for n in ("to_q", "to_k", "to_v", "to_out.0"):
+            _rand_linear(sd, f"{p}.attn2.{n}", dim, dim, g, device)
+        for n in ("norm_q", "norm_k"):
+            sd[f"{p}.attn2.{n}.weight"] = (1 + 0.1 * torch.randn(head_dim, generator=g, device=device)).to(torch.bfloat16)
+    for ff in (("ff",) if context_pre_only else ("ff", "ff_context")):
+        _rand_linear(sd, f"{p}.{ff}.net.0.proj", 4 * dim, dim, g, device)
+        _rand_linear(sd, f"{p}.{ff}.net.2", dim, 4 * dim, g, device)
+    return sd
+
+
+class SD3TransformerModelCore:
+    """fastdm/model/sd35.py:202-424 (SD3.5-medium defaults: 24 MMDiT blocks, d = 1536, 24 x 64 heads, image-only
+    second attention in layers 0-12, the last block `context_pre_only`). Single GPU (BASELINE configs[1])."""
+
+    def __init__(self, patch_size=2, in_channels=16, num_layers=24, attention_head_dim=64, num_attention_heads=24,
+                 joint_attention_dim=4096, pooled_projection_dim=2048, out_channels=16, pos_embed_max_size=384,
+                 dual_attention_layers=tuple(range(13)), quant_dtype=torch.float8_e4m3fn, device="cuda", seed=0,
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        self.heads, self.hd = num_attention_heads, attention_head_dim
+        self.inner_dim = d = self.heads * self.hd
+        self.patch_size, self.out_channels, self.pos_max = patch_size, out_channels, pos_embed_max_size
+        g = torch.Generator(device=device).manual_seed(seed)
+        sd = state_dict
+
+        def part(make):
+            return sd if sd is not None else make()
+
+        def pre():
+            s = {}
+            s["pos_embed.proj.weight"] = (torch.randn(d, in_channels, patch_size, patch_size, generator=g, device=device) * 0.05).to(torch.bfloat16)
+            s["pos_embed.proj.bias"] = torch.zeros(d, device=device, dtype=torch.bfloat16)
+            s["pos_embed.pos_embed"] = (torch.randn(1, pos_embed_max_size ** 2, d, generator=g, device=device) * 0.02).to(torch.bfloat16)
+            for n in ("timestep_embedder", "text_embedder"):
+                _rand_linear(s, f"time_text_embed.{n}.linear_1", d, 256 if n == "timestep_embedder" else pooled_projection_dim, g, device)
+                _rand_linear(s, f"time_text_embed.{n}.linear_2", d, d, g, device)
+            _rand_linear(s, "context_embedder", d, joint_attention_dim, g, device)
+            _rand_linear(s, "norm_out.linear", 2 * d, d, g, device)
+            _rand_linear(s, "proj_out", patch_size * patch_size * out_channels, d, g, device)
+            return s
+
+        s = part(pre)
+        self.proj_weight = s["pos_embed.proj.weight"].to(device)
+        self.proj_bias = s["pos_embed.proj.bias"].to(device)
+        self.pos_embed = s["pos_embed.pos_embed"].to(device)
+        self.timestep_embedder = _MLP(s, "time_text_embed.timestep_embedder", "silu", device)
+        self.text_embedder = _MLP(s, "time_text_embed.text_embedder", "silu", device)
+        self.context_embedder = load_linear(s, ["context_embedder"], None, device)
+        self.norm_out_linear = load_linear(s, ["norm_out.linear"], quant_dtype, device)     # quantised in the reference (sd35.py:327-328)
+        self.proj_out = load_linear(s, ["proj_out"], quant_dtype, device)
+        self.transformer_blocks: List[JointTransformerBlock] = []
+        for i in range(num_layers):
+            p, last, dual = f"transformer_blocks.{i}", i == num_layers - 1, i in dual_attention_layers
+            self.transformer_blocks.append(JointTransformerBlock(
+                part(lambda: random_sd3_block_sd(p, d, self.hd, g, device, last, dual)), p, self.heads, self.hd, quant_dtype,
+                device, context_pre_only=last, use_dual_attention=dual))
+
+    def _patch_embed(self, latent):
+        """PatchEmbed.forward with the centre-cropped learned position table (layer/embeddings.py)."""
+        h, w = latent.shape[-2] // self.patch_size, latent.shape[-1] // self.patch_size
+        x = F.conv2d(latent, self.proj_weight, self.proj_bias, stride=self.patch_size).flatten(2).transpose(1, 2)
+        top, left = (self.pos_max - h) // 2, (self.pos_max - w) // 2
+        pos = self.pos_embed.view(1, self.pos_max, self.pos_max, -1)[:, top:top + h, left:left + w].reshape(1, h * w, -1)
+        return (x + pos).to(latent.dtype).contiguous(), h, w
+
+    def forward(self, hidden_states, encoder_hidden_states, pooled_projections, timestep):
+        dt = hidden_states.dtype
+        x, h, w = self._patch_embed(hidden_states)                                               # sd35.py:380
+        temb = self.timestep_embedder.forward(
+            get_timestep_embedding(timestep, 256, flip_sin_to_cos=True, downscale_freq_shift=0).to(dt))
+        temb = temb + self.text_embedder.forward(pooled_projections)                             # :381
+        enc = self.context_embedder.forward(encoder_hidden_states)                               # :382
+        for block in self.transformer_blocks:                                                    # :394-400
+            enc, x = block.forward(x, enc, temb)
+        emb = self.norm_out_linear.forward(F.silu(temb).to(dt))
+        scale, shift = torch.chunk(emb, 2, dim=1)
+        x = F.layer_norm(x, (self.inner_dim,), None, None, 1e-6) * (1 + scale)[:, None, :] + shift[:, None, :]
+        x = self.proj_out.forward(x.to(dt))
+        ps, c = self.patch_size, self.out_channels                                               # unpatchify :411-424
+        x = x.reshape(x.shape[0], h, w, ps, ps, c)
+        x = torch.einsum("nhwpqc->nchpwq", x)
+        return (x.reshape(x.shape[0], c, h * ps, w * ps),)

@@ -300,3 +300,22 @@ def test_qwen_image_model_forward_and_rope_table():
     y2 = model.forward(lat, txt, ts, (f, h, w))[0].float()
     cos = torch.nn.functional.cosine_similarity(y.flatten(), y2.flatten(), dim=0).item()
     assert cos > 0.9999, cos
+
+
+def test_sd3_model_core_forward():
+    """Whole SD3.5-style core (3 layers: dual-attention, plain, context_pre_only last): runs end to end, finite,
+    the right output shape, and deterministic."""
+    from fastdm_b200.models import SD3TransformerModelCore
+
+    dev, bf = "cuda", torch.bfloat16
+    model = SD3TransformerModelCore(num_layers=3, attention_head_dim=64, num_attention_heads=4, joint_attention_dim=256,
+                                    pooled_projection_dim=128, pos_embed_max_size=64, dual_attention_layers=(0,),
+                                    device=dev, seed=9)
+    g = torch.Generator().manual_seed(4)
+    lat = torch.randn(2, 16, 48, 64, generator=g).to(bf).to(dev)
+    txt = torch.randn(2, 77, 256, generator=g).to(bf).to(dev)
+    pooled = torch.randn(2, 128, generator=g).to(bf).to(dev)
+    ts = torch.tensor([500.0, 500.0]).to(bf).to(dev)
+    y = model.forward(lat, txt, pooled, ts)[0]
+    assert y.shape == lat.shape and bool(torch.isfinite(y.float()).all())
+    assert torch.equal(y, model.forward(lat, txt, pooled, ts)[0])
