@@ -82,6 +82,39 @@ class QLinear:
         else:
             raise ValueError(f"Unsupported quantization type: {quant_type}")
 
+    # ---- pre-quantised weights: quantise once, cache, reload without the bf16 weights ----
+    def export_quantized(self) -> dict:
+        """Everything `forward` needs, on the CPU: 8-bit codes in the [N, K] storage order (as raw bytes, so the
+        file does not depend on float8 serialisation), per-channel scales, INT8 column sums, bias."""
+        w_nk = self.weight.transpose(0, 1).contiguous()
+        qt = self.quant_type
+        d = dict(quant_type={None: "none", torch.float8_e4m3fn: "fp8_e4m3", torch.int8: "int8"}[qt],
+                 in_features=self.in_features, out_features=self.out_features, dtype=str(self.dtype).split(".")[-1],
+                 weight=(w_nk.view(torch.uint8) if qt is not None else w_nk).cpu(),
+                 bias=None if self.bias is None else self.bias.cpu())
+        if qt is not None:
+            d["scale"] = self.weight_quant_scale.cpu()
+        if self.weight_asym_sumcol is not None:
+            d["sumcol"] = self.weight_asym_sumcol.cpu()
+        return d
+
+    @classmethod
+    def from_quantized(cls, d: dict, device="cuda") -> "QLinear":
+        dt = getattr(torch, d["dtype"])
+        lin = cls(d["in_features"], d["out_features"], bias=d["bias"] is not None, data_type=dt, device_type=device)
+        w = d["weight"].to(device)
+        if d["quant_type"] == "fp8_e4m3":
+            w = w.view(torch.float8_e4m3fn)
+        elif d["quant_type"] == "int8":
+            w = w.view(torch.int8)
+        lin.weight = w.transpose(0, 1)
+        lin.bias = None if d["bias"] is None else d["bias"].to(device)
+        if "scale" in d:
+            lin.weight_quant_scale = d["scale"].to(device)
+        if "sumcol" in d:
+            lin.weight_asym_sumcol = d["sumcol"].to(device)
+        return lin
+
     def forward(self, input_tensor, act: Optional[str] = None, out: Optional[torch.Tensor] = None,
                 gate: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
                 rows_per_batch: int = 1, round_steps: bool = True):
@@ -134,3 +167,12 @@ class FeedForward:
         hq = quantize(h.reshape(-1, h.shape[-1]), self.ff_out_proj.quant_type)
         return self.ff_out_proj.forward(hq, gate=gate, residual=residual, rows_per_batch=rows_per_batch,
                                         round_steps=round_steps, out=out)
+
+
+def save_quantized(linears: dict, path: str):
+    """{name: QLinear} -> one file of pre-quantised weights (e4m3 / int8 codes + fp32 scales + int32 column sums)."""
+    torch.save({name: lin.export_quantized() for name, lin in linears.items()}, path)
+
+
+def load_quantized(path: str, device="cuda") -> dict:
+    return {name: QLinear.from_quantized(d, device) for name, d in torch.load(path, map_location="cpu").items()}

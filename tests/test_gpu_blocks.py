@@ -319,3 +319,20 @@ def test_sd3_model_core_forward():
     y = model.forward(lat, txt, pooled, ts)[0]
     assert y.shape == lat.shape and bool(torch.isfinite(y.float()).all())
     assert torch.equal(y, model.forward(lat, txt, pooled, ts)[0])
+
+
+@pytest.mark.parametrize("quant", [torch.float8_e4m3fn, torch.int8, None])
+def test_prequantized_weight_cache_roundtrip(quant, tmp_path):
+    """QLinear -> export -> file -> reload gives the bit-identical forward without touching the bf16 weights again."""
+    from fastdm_b200.layers import QLinear, load_linear, load_quantized, save_quantized
+
+    g = torch.Generator().manual_seed(3)
+    sd = {"a.weight": (torch.randn(192, 256, generator=g) * 0.05).to(torch.bfloat16), "a.bias": torch.randn(192, generator=g).to(torch.bfloat16),
+          "b.weight": (torch.randn(64, 256, generator=g) * 0.05).to(torch.bfloat16), "b.bias": torch.randn(64, generator=g).to(torch.bfloat16)}
+    lin = load_linear(sd, ["a", "b"], quant, "cuda")          # fused along N like a qkv projection
+    path = str(tmp_path / "w.pt")
+    save_quantized({"ab": lin}, path)
+    lin2 = load_quantized(path, "cuda")["ab"]
+    assert isinstance(lin2, QLinear) and lin2.quant_type == quant
+    x = torch.randn(70, 256, generator=g).to(torch.bfloat16).cuda()
+    assert torch.equal(lin.forward(x), lin2.forward(x))
