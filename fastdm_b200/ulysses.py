@@ -84,13 +84,24 @@ class UlyssesAttention:
         dist.all_gather(parts, x.contiguous(), group=self.group)
         return torch.cat(parts, dim=dim)
 
+    def local_mask(self, sparse_mask: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        """A block mask given for all H heads ([B, H, nbq, nbk]) -> the [B, H/P, nbq, nbk] slice of this rank's
+        heads (a mask that already has H/P heads is taken as is)."""
+        if sparse_mask is None or self.P == 1 or sparse_mask.shape[1] == self.H // self.P:
+            return sparse_mask
+        if sparse_mask.shape[1] != self.H:
+            raise ValueError(f"sparse mask has {sparse_mask.shape[1]} heads, expected {self.H} or {self.H // self.P}")
+        hp = self.H // self.P
+        return sparse_mask[:, self.rank * hp:(self.rank + 1) * hp].contiguous()
+
     # ---- attention on a local fused qkv shard ------------------------------------------------------
     def attention(self, qkv_local: torch.Tensor, scale: Optional[float] = None, sparse_mask=None,
                   block_q: int = 128, block_k: int = 64,
                   attention_fn: Optional[Callable] = None) -> torch.Tensor:
         """qkv_local [1, S/P, 3*H*hd] (q|k|v, q and k already normalised + rotated with THIS shard's
         positions) -> attention output for the local tokens [1, S/P, H*hd].
-        sparse_mask, if given, is the [1, H/P, nbq, nbk] mask of this rank's heads."""
+        sparse_mask, if given, is the [1, H, nbq, nbk] mask of all heads (sliced here) or the [1, H/P, nbq, nbk]
+        mask of this rank's heads."""
         H, hd, P = self.H, self.hd, self.P
         d = H * hd
         if qkv_local.shape[0] != 1:
@@ -105,7 +116,7 @@ class UlyssesAttention:
         if attention_fn is not None:
             o = attention_fn(q, k, v, H // P, hd, scale)
         else:
-            o = ops.attention(q, k, v, H // P, hd, scale, sparse_mask, block_q, block_k)
+            o = ops.attention(q, k, v, H // P, hd, scale, self.local_mask(sparse_mask), block_q, block_k)
         back, _ = self._a2a(o.reshape(P, S_loc, dp).contiguous())  # chunk p: head group p of my tokens
         return _unpack(back, H, hd, 1).view(1, S_loc, d)
 
@@ -140,6 +151,6 @@ class UlyssesAttention:
             cur.wait_event(e)
         S_loc = recvs[0].shape[1]
         q, k, v = (r.view(1, P * S_loc, dp) for r in recvs)
-        o = ops.attention(q, k, v, H // P, hd, scale, sparse_mask, block_q, block_k)
+        o = ops.attention(q, k, v, H // P, hd, scale, self.local_mask(sparse_mask), block_q, block_k)
         back, _ = self._a2a(o.reshape(P, S_loc, dp).contiguous())
         return _unpack(back, H, hd, 1).view(1, S_loc, d)
