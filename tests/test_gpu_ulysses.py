@@ -59,6 +59,18 @@ for overlap in (True, False):
     err = (full.float() - ref.float()).abs().max().item()
     cos = torch.nn.functional.cosine_similarity(full.flatten().double(), ref.flatten().double(), dim=0).item()
     res[overlap] = (err, cos)
+# block-sparse self-attention with a DIFFERENT mask per head: every rank must pick its own heads' masks
+gm = torch.Generator().manual_seed(5)
+mask = (torch.rand(1, H, (S + 127) // 128, (S + 63) // 64, generator=gm) < 0.6).to(torch.int8)
+mask[:, :, :, 0] = 1
+mask = mask.to(dev)
+ref_s = blk.forward(x, enc, temb, rope, mask)
+for overlap in (True, False):
+    y = blk.forward(xs, enc, temb, rope, mask, ulysses=ul, pos0=rank * xs.shape[1], overlap=overlap)
+    full = ul.gather_tokens(y, 1)
+    err = (full.float() - ref_s.float()).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(full.flatten().double(), ref_s.flatten().double(), dim=0).item()
+    res["sparse_%s" % overlap] = (err, cos)
 if rank == 0:
     print("ULYSSES_RESULT", res, float(ref.float().abs().max()))
 dist.barrier(); dist.destroy_process_group()
