@@ -349,7 +349,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (CG == 2) tc_commit_cg2_elect(bar, 0b11);  // the same barrier in both CTAs of the pair
         else tc_commit_elect(bar);
       };
-      // `probe` runs after the 4th and 6th MMA of a group -- with the queue full, i.e. for free
+      // `probe` runs after the 7th MMA of a group -- with the queue full, i.e. for free (one late probe measured
+      // no worse than two earlier ones and succeeds more often)
       auto issue_qk = [&](int x, uint32_t k_smem, auto&& probe) {
         const uint64_t k_desc = make_desc_kmajor_sw128(k_smem);
         const uint64_t q_desc = q_desc_of(x);
@@ -360,7 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           // a CTA of a pair holds kKvTile / 2 keys per head-dim panel
           const uint64_t koff = (uint64_t)(((ks / 4) * (kKvTile / CG * 128) + (ks % 4) * 32) >> 4);
           umma_ss<kKind, CG, true>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
-          if (ks == 3 || ks == 5) probe();
+          if (ks == 6) probe();
         }
       };
       auto no_probe = [] {};
@@ -380,7 +381,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           } else {
             umma_ts<kKind, true>(tO, tS + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
           }
-          if (ks == (kKvTile / kKeysPerPV) / 2 - 1 || ks == (kKvTile / kKeysPerPV) * 3 / 4 - 1) probe();
+          if (ks == (kKvTile / kKeysPerPV) * 7 / 8 - 1) probe();
         }
       };
       auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kKvBytes; };
