@@ -452,6 +452,14 @@ def main():
         extra["flux"] = dict(config=workload_config("flux", 1), ms_per_step=fms, e2e_ms=fe2e, h2d_bytes_per_step=fh2d,
                              d2h_bytes_per_step=fd2h, attention_tflops=froof["achieved"],
                              step_tflops=165.4e3 / fms)
+        # the same model at 1024x1024 (4096 image + 512 text tokens), the "FLUX 1024^2" of BASELINE.json's metric line
+        sq = {k: v for k, v in fhost.items()}
+        sq["latent"] = fhost["latent"][:, :4096].contiguous().pin_memory()
+        sq["img_ids"] = fhost["img_ids"][:4096].contiguous().pin_memory()
+        sfn = step_fn("flux", fmodel, None)
+        if not args.no_graph:
+            sfn = GraphedStep(sfn, to_device(sq, device))
+        extra["flux"]["ms_per_step_1024x1024"] = timed_steps(sfn, to_device(sq, device), 10, 3, 1, device)
         del fmodel
 
     if rank != 0:
