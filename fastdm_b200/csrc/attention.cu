@@ -173,6 +173,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr bool F16 = DT == kDtF16;
   static_assert(CG == 1 || (PS && HD == 128 && ES == 2), "the CTA-pair variant is built for hd 128, 16-bit operands, P in smem");
   using S = AttnSmem<HD, ES, PS, CG>;
+  // hd 64 leaves half of each O block of TMEM unused: P goes there (PT) instead of over S, so -- exactly as with
+  // P in shared memory (PS) -- S_X is free as soon as the softmax warps hold it in registers and QK_X(t+1) is
+  // issued ahead of PV_X(t) (DEC): no smem needed, P still feeds a TS MMA.
+  constexpr bool PT = !PS && HD == 64 && ES == 2;
+  constexpr bool DEC = PS || PT;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -313,7 +318,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         ++u;
       };
-      if (PS) {
+      if (DEC) {
         // ring order = order of first use by the MMA warp: K(0), then K(t+1), V(t) for every active tile t
         int j = next_active(0);
         if (j < p.n_kv_tiles) load_tile(&tmap_k, j);
@@ -368,7 +373,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       auto issue_pv = [&](int x, uint32_t v_smem, bool accumulate, auto&& probe) {
         const uint64_t v_desc = make_desc_mnmajor_sw128(v_smem, kKvTile * 128, 1024);
         const uint64_t p_desc = p_desc_of(x);
-        const uint32_t tS = tS_of(x), tO = tO_of(x);
+        const uint32_t tO = tO_of(x);
+        const uint32_t tP = PT ? tO + 64u : tS_of(x);  // PT: columns [320,384) / [448,512), else over S_X
 #pragma unroll
         for (int ks = 0; ks < kKvTile / kKeysPerPV; ++ks) {
           // kKeysPerPV keys = that many 128-byte rows of V; the matching slice of P is 32 bytes of its
@@ -379,7 +385,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const uint64_t poff = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
             umma_ss<kKind, CG, true>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
           } else {
-            umma_ts<kKind, true>(tO, tS + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
+            umma_ts<kKind, true>(tO, tP + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
           }
           if (ks == (kKvTile / kKeysPerPV) * 7 / 8 - 1) probe();
         }
@@ -396,8 +402,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(q_full, 0);
         tc_fence_after();
         wait_full(0);
-        if (PS) {
-          // P travels through shared memory, so S_X is free again as soon as the softmax warps hold it in
+        if (DEC) {
+          // P travels through shared memory (or spare TMEM columns), so S_X is free again as soon as the softmax warps hold it in
           // registers: QK_X(t+1) is issued ahead of PV_X(t) and the only per-tile dependency chain left is
           // the softmax itself. Per active tile t the groups go QK_A(t+1), PV_A(t), QK_B(t+1), PV_B(t); ring
           // items (order of first use): K(0) | K(t+1), V(t) | ... While a group is being issued the barriers
@@ -553,6 +559,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_off = (uint32_t)(lane_group * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + (uint32_t)(x * 128);
     const uint32_t tO = tmem_base + lane_off + 256u + (uint32_t)(x * 128);
+    const uint32_t tP = PT ? tO + 64u : tS;  // where P goes in TMEM (unless it goes to shared memory)
     // this thread's row of the K-major, 128B-swizzled P tile in shared memory (PS)
     const uint32_t p_row = base + S::kPOff + (uint32_t)x * S::kPBytes + (uint32_t)row_in_tile * 128u;
     const uint32_t p_sw = (uint32_t)(row_in_tile & 7);
@@ -569,8 +576,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       trace_ev(p, tr, x, 1, t);
       tc_fence_after();
       // PS: has PV_X(t-1) finished reading the P tile? Probed here, needed only at the first store of P
-      bool p_free = !PS || t == 0;
-      if (PS && t > 0) p_free = mbar_test_wait(o_done(x), (t - 1) & 1u);
+      bool p_free = !DEC || t == 0;
+      if (DEC && t > 0) p_free = mbar_test_wait(o_done(x), (t - 1) & 1u);
       const int valid = p.Sk - j * kKvTile;  // keys of this tile inside the sequence
       bool seg0 = true, seg1 = true;
       if (has_mask) {
@@ -586,7 +593,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool dead = has_mask && __all_sync(0xffffffffu, !seg0 && !seg1);
       bool tmem_dirty = false;
       if (dead) {
-        if (PS) {
+        if (DEC) {
           tc_fence_before();
           if (CG == 2) {
             __syncwarp();
@@ -595,6 +602,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mbar_arrive(s_free(x));
           }
           if (!p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+        }
+        if (PS) {
 #pragma unroll
           for (int q = 0; q < kKvTile * ES / 16; ++q)
             sts128(p_row + (uint32_t)((q >> 3) * (kQTile * 128)) + ((((uint32_t)(q & 7)) ^ p_sw) << 4), 0u, 0u, 0u, 0u);
@@ -603,7 +612,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) z[i] = 0u;
 #pragma unroll
-          for (int c = 0; c < kKvTile * ES / 64; ++c) tmem_st_32x16(tS + (uint32_t)(c * 16), z);
+          for (int c = 0; c < kKvTile * ES / 64; ++c) tmem_st_32x16(tP + (uint32_t)(c * 16), z);
         }
       } else {
       // -inf on keys beyond the sequence end and on masked 64-key segments
@@ -622,7 +631,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld_32x32(tS + 64u, s2);
       tmem_ld_32x32(tS + 96u, s3);
       tmem_ld_wait();
-      if (PS) {
+      if (DEC) {
         // S_X is in registers: the MMA warp may overwrite it with the next tile's scores right away
         tc_fence_before();
         if (CG == 2) {
@@ -663,7 +672,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       trace_ev(p, tr, x, 3, t);
       // the shared-memory P tile is read by PV_X(t-1) until o_done(x) completes its phase
-      if (PS && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+      if (DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
       // ---- P = exp2(S*scale - m): over the first columns of S_X in TMEM, or into the P tile in smem ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
@@ -701,7 +710,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int q = 0; q < 2; ++q)
               sts128(p_row + ((((uint32_t)(c * 2 + q)) ^ p_sw) << 4), p8[4 * q], p8[4 * q + 1], p8[4 * q + 2], p8[4 * q + 3]);
           } else {
-            tmem_st_32x8(tS + (uint32_t)(c * 8), p8);
+            tmem_st_32x8(tP + (uint32_t)(c * 8), p8);
           }
         } else if (PS) {
           // 32 keys = 64 bytes = four 16-byte chunks of this row in panel c/2 (64 keys per 128-byte row)
@@ -710,7 +719,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             sts128(p_row + (uint32_t)((c >> 1) * (kQTile * 128)) + ((((uint32_t)((c & 1) * 4 + q)) ^ p_sw) << 4),
                    pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         } else {
-          tmem_st_32x16(tS + (uint32_t)(c * 16), pk);
+          tmem_st_32x16(tP + (uint32_t)(c * 16), pk);
         }
       };
       emit(s0, 0);
