@@ -313,13 +313,116 @@ def attention_roofline(wl, world, device, pk):
     ms = e0.elapsed_time(e1) / n
     flops = 4.0 * H * S * S * hd
     ach = flops / ms / 1e9
-    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture
-    # (profiles/r01_ncu_full_summary.txt): only the N=1 launch shapes were captured.
-    traffic = {("wan", 1): 4.403e9, ("flux", 1): 1.927e8}.get((wl, world))
+    # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture: profiles/attn_traffic.json
+    # (written from the .ncu-rep by tools/ncu_traffic.py; only the N=1 launch shapes were captured)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "attn_traffic.json")) as f:
+            traffic = json.load(f).get(f"{wl}_n{world}", {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
     return dict(bound="tensor", kernel="attn_fwd_kernel<128,bf16>", achieved=ach, peak=pk["bf16"], unit="TFLOP/s",
                 frac=ach / pk["bf16"], traffic=traffic, traffic_unit="bytes/launch (dram read+write, ncu --set full)",
                 algorithmic_bytes=4.0 * S * H * hd * 2, ms_per_launch=ms, flops_per_launch=flops,
                 peak_source=pk["src"] + ", bf16 burst (kernel timed alone)")
+
+
+def _cuda_ms(fn, iters, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def gemm_roofline(wl, device, pk):
+    """"FP8 GEMM TFLOPS/peak" (BASELINE.json metric): the workload's largest linear (ff1: Wan 80640x5120x13824,
+    FLUX 8704x3072x12288) through ops.fp8_matmul (per-token x per-channel scales, bias, bf16 out), timed alone with
+    CUDA events; outputs (>= 0.2 GB) exceed L2. Also the same call through torch._scaled_mm (cuBLASLt rowwise)."""
+    from fastdm_b200 import ops
+
+    M, K, N = (80640, 5120, 13824) if wl == "wan" else (8704, 3072, 12288)
+    g = torch.Generator(device=device).manual_seed(3)
+    a = torch.randn(M, K, device=device, generator=g).to(torch.float8_e4m3fn)
+    b = torch.randn(N, K, device=device, generator=g).to(torch.float8_e4m3fn).t()
+    sa = torch.rand(M, 1, device=device) * 0.01
+    sb = torch.rand(N, 1, device=device)
+    bias = torch.randn(N, device=device).to(torch.bfloat16)
+    out = torch.empty(M, N, device=device, dtype=torch.bfloat16)
+    it = 5 if wl == "wan" else 30
+    ms = _cuda_ms(lambda: ops.fp8_matmul(a, b, sa, sb, torch.bfloat16, bias, out=out), it, 2)
+    try:
+        ms_t = _cuda_ms(lambda: torch._scaled_mm(a, b, sa, sb.t(), bias, out_dtype=torch.bfloat16), it, 2)
+    except Exception as e:  # noqa: BLE001
+        print("bench: torch._scaled_mm failed:", str(e)[:200], file=sys.stderr)
+        ms_t = None
+    fl = 2.0 * M * N * K
+    tf = fl / ms / 1e9
+    return dict(kernel="gemm_w8a8_kernel<fp8>", shape=[M, K, N], ms=ms, tflops=tf, peak=2 * pk["bf16"], frac=tf / (2 * pk["bf16"]),
+                peak_source="2 x measured bf16 burst (" + pk["src"] + "); nominal dense fp8 4500", frac_of_nominal=tf / 4500.0,
+                torch_scaled_mm_ms=ms_t, torch_scaled_mm_tflops=(fl / ms_t / 1e9) if ms_t else None)
+
+
+def gpu_torch_baseline(wl, device, ours_step_ms, roof, gemm):
+    """The reference's B200-runnable backend (KERNEL_BACKEND=torch: fastdm/kernel/torch/matrixmul.py:33
+    `torch._scaled_mm` rowwise, attention.py:38-40 `F.scaled_dot_product_attention`, unfused elementwise ops), as
+    restated in oracle/blocks_ref.py, moved to this GPU: ONE full-size block of every block type of the workload,
+    CUDA-event timed, times the block count (embedders / output projection, < 1 % of a step, are not in the
+    estimate). A measured baseline only -- nothing of it is on the product path."""
+    from oracle import blocks_ref as B
+
+    bf, quant = torch.bfloat16, torch.float8_e4m3fn
+    g = torch.Generator(device=device).manual_seed(0)
+    rnd = lambda *sh: torch.randn(*sh, device=device, generator=g).to(bf)  # noqa: E731
+    cuda_sd = lambda sd: {k: v.to(device) for k, v in sd.items()}  # noqa: E731
+    if wl == "wan":
+        d, H, hd = WAN["heads"] * WAN["head_dim"], WAN["heads"], WAN["head_dim"]
+        S = WAN["frames"] * (WAN["height"] // 2) * (WAN["width"] // 2)
+        blk = B.WanTransformerBlockRef(cuda_sd(B.wan_block_state_dict("blocks.0", d, WAN["ffn"], seed=1)), "blocks.0", H, hd, quant)
+        x, enc, temb = rnd(1, S, d), rnd(1, WAN["text_len"], d), rnd(1, 6, d)
+        cos = torch.rand(1, S, 1, hd, device=device, generator=g)
+        sin = torch.rand(1, S, 1, hd, device=device, generator=g)
+        with torch.no_grad():
+            t_blk = _cuda_ms(lambda: blk.forward(x, enc, temb, (cos, sin)), 2, 1)
+        step = WAN["layers"] * t_blk
+        blocks = dict(wan_block_ms=t_blk, count=WAN["layers"])
+        del blk, x, cos, sin
+    else:
+        d, H, hd = FLUX["heads"] * FLUX["head_dim"], FLUX["heads"], FLUX["head_dim"]
+        S = FLUX["img_tokens"] + FLUX["txt_tokens"]
+        dbl = B.FluxTransformerBlockRef(cuda_sd(B.flux_double_state_dict("transformer_blocks.0", d, hd, seed=1)),
+                                        "transformer_blocks.0", H, hd, quant)
+        sgl = B.FluxSingleTransformerBlockRef(cuda_sd(B.flux_single_state_dict("single_transformer_blocks.0", d, hd, seed=2)),
+                                              "single_transformer_blocks.0", H, hd, quant)
+        xi, xt, temb, rope = rnd(1, FLUX["img_tokens"], d), rnd(1, FLUX["txt_tokens"], d), rnd(1, d), \
+            torch.rand(S, hd, device=device, generator=g).to(bf)
+        xs = rnd(1, S, d)
+        with torch.no_grad():
+            t_d = _cuda_ms(lambda: dbl.forward(xi, xt, temb, rope), 10, 2)
+            t_s = _cuda_ms(lambda: sgl.forward(xs, temb, rope), 10, 2)
+        step = FLUX["double"] * t_d + FLUX["single"] * t_s
+        blocks = dict(flux_double_block_ms=t_d, flux_single_block_ms=t_s, count=[FLUX["double"], FLUX["single"]])
+        del dbl, sgl
+    torch.cuda.empty_cache()
+    # the reference backend's attention call on the dominant shape (attention.py:33-40: [B,H,S,hd] views of NHD tensors)
+    Hh = H
+    q, k, v = (rnd(1, S, Hh * hd).view(1, S, Hh, hd).transpose(1, 2) for _ in range(3))
+    t_att = _cuda_ms(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), 2 if wl == "wan" else 20, 1)
+    att_tf = 4.0 * Hh * S * S * hd / t_att / 1e9
+    del q, k, v
+    torch.cuda.empty_cache()
+    return dict(backend="reference torch backend on this GPU (torch._scaled_mm rowwise fp8 + F.scaled_dot_product_attention + "
+                        "unfused elementwise; oracle/blocks_ref.py on cuda), one full-size block x block count",
+                step_ms_est=step, attention_ms=t_att, attention_tflops=att_tf, gemm_ms=gemm.get("torch_scaled_mm_ms"),
+                gemm_tflops=gemm.get("torch_scaled_mm_tflops"), **blocks,
+                vs_torch_backend=dict(step=step / ours_step_ms, attention=t_att / roof["ms_per_launch"],
+                                      gemm=(gemm["torch_scaled_mm_ms"] / gemm["ms"]) if gemm.get("torch_scaled_mm_ms") else None,
+                                      note="torch-backend time / our time on the same box: > 1 means we are faster"))
 
 
 _JSON_FD = None
@@ -360,6 +463,7 @@ def main():
     ap.add_argument("--no-sparse", action="store_true", help="skip the radial-sparse Wan variant at N=1")
     ap.add_argument("--no-graph", action="store_true", help="launch the FLUX step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the reference-torch-backend-on-this-GPU leg at N=1")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -423,6 +527,10 @@ def main():
         extra["a2a_exposed_ms"] = ms - ms_stub
         extra["ms_per_step_comm_stubbed"] = ms_stub
     roof = attention_roofline(wl, world, device, pk)
+    if rank == 0 and world == 1:
+        extra["gemm"] = gemm_roofline(wl, device, pk)
+        if not args.no_torch_baseline and not args.layers:
+            extra["gpu_torch_baseline"] = gpu_torch_baseline(wl, device, ms, roof, extra["gemm"])
 
     if rank == 0 and wl == "wan" and world == 1 and not args.no_sparse and not args.layers:
         # BASELINE configs[4] "dense vs Sparge sparse attention": the same step with the reference's radial block
@@ -451,7 +559,9 @@ def main():
         froof = attention_roofline("flux", 1, device, pk)
         extra["flux"] = dict(config=workload_config("flux", 1), ms_per_step=fms, e2e_ms=fe2e, h2d_bytes_per_step=fh2d,
                              d2h_bytes_per_step=fd2h, attention_tflops=froof["achieved"],
-                             step_tflops=165.4e3 / fms)
+                             step_tflops=165.4e3 / fms, gemm=gemm_roofline("flux", device, pk))
+        if not args.no_torch_baseline:
+            extra["flux"]["gpu_torch_baseline"] = gpu_torch_baseline("flux", device, fms, froof, extra["flux"]["gemm"])
         # the same model at 1024x1024 (4096 image + 512 text tokens), the "FLUX 1024^2" of BASELINE.json's metric line
         sq = {k: v for k, v in fhost.items()}
         sq["latent"] = fhost["latent"][:, :4096].contiguous().pin_memory()

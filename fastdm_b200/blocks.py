@@ -396,6 +396,10 @@ class WanTransformerBlock:
         `pos0` its first position in the full sequence; `rotary_emb` covers the full sequence."""
         B, S, d = hidden_states.shape
         H, hd, qt = self.heads, self.hd, self.quant_type
+        if ulysses is not None and ulysses.P > 1 and B != 1:
+            # every rank raises (B is the same on all of them), so no rank is left waiting in a collective
+            raise NotImplementedError("WanTransformerBlock: the Ulysses path is written for batch 1 "
+                                      "(CFG halves are separate forwards); got batch %d" % B)
         shift_msa, scale_msa, gate_msa, c_shift_msa, c_scale_msa, c_gate_msa = (
             self.scale_shift_table + temb.float()).chunk(6, dim=1)                      # wan.py:88-91 (fp32)
         r2 = lambda t: t.reshape(B, d).contiguous()  # noqa: E731

@@ -30,6 +30,8 @@
 // Replaces the library routes of fastdm/kernel/cuda/attention.py:149-261.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "sm100.cuh"
 
 namespace fdm {
@@ -67,6 +69,7 @@ struct AttnParams {
   int n_kv_tiles;
   int mask_bq, mask_bk, nbq, nbk;
   float scale_log2;
+  int issue_mode;    // MMA issuer of the P-outside-S kernels: 0 = fixed group order, 1 = greedy (whatever is ready), 2 = greedy + back-off
   long long* trace;  // debug: per-event clock64 stamps of CTA (0,0,0), or nullptr
 };
 
@@ -165,12 +168,14 @@ __device__ __forceinline__ void ex2_emulated_pair(uint64_t y, float& p0, float& 
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE>
+template <int HD, int DT, int EMUX, bool PS, int CG, bool MASKED, bool TRACE>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
   constexpr int ES = DT == kDtE4M3 ? 1 : 2;  // operand element size
   constexpr bool F16 = DT == kDtF16;
+  constexpr int EMU = EMUX & 63;           // exponentials per 32 that run on the FMA pipe
+  constexpr bool LS = (EMUX & 64) != 0;    // late store: the whole P tile is packed in registers before it is written
   static_assert(CG == 1 || (PS && HD == 128 && ES == 2), "the CTA-pair variant is built for hd 128, 16-bit operands, P in smem");
   using S = AttnSmem<HD, ES, PS, CG>;
   // hd 64 leaves half of each O block of TMEM unused: P goes there (PT) instead of over S, so -- exactly as with
@@ -402,7 +407,70 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         mbar_wait(q_full, 0);
         tc_fence_after();
         wait_full(0);
-        if (DEC) {
+        if (DEC && p.issue_mode != 0) {
+          // Greedy issue. The four MMA groups of a step -- QK_A(n), QK_B(n), PV_A(m), PV_B(m) -- depend on the two
+          // softmax warpgroups independently: QK_X(n) needs S_X(n-1) in registers (s_free) and K(n) in the ring,
+          // PV_X(m) needs P_X(m) (p_ready) and V(m). In a fixed order one tile's late softmax holds back the other
+          // tile's QK, and with S single-buffered every such delay is a softmax warpgroup idling on s_full. Here
+          // the thread issues whichever group is ready, QK first (it is what feeds a softmax warpgroup), so each
+          // Q tile runs at its own softmax's pace and the tensor pipe takes whatever there is.
+          // Ring items (TMA order): K(0) | K(t+1), V(t) | ...: K(n) = 2n-1 (n >= 1), V(m) = 2m+2, or 2m+1 for the last tile.
+          uint32_t T = (uint32_t)p.n_kv_tiles;
+          if (has_mask) {
+            const uint32_t* words = reinterpret_cast<const uint32_t*>(flags);
+            T = 0;
+            for (int w = 0; w < (p.n_kv_tiles + 31) / 32; ++w) T += (uint32_t)__popc(words[w]);
+          }
+          auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
+          issue_qk(0, stage_smem(0), no_probe);
+          commit(s_full(0));
+          issue_qk(1, stage_smem(0), no_probe);
+          commit(s_full(1));
+          commit(kv_empty(0));
+          uint32_t qk0 = 1, qk1 = 1, pv0 = 0, pv1 = 0;  // next tile of each group kind per Q tile
+          auto try_qk = [&](int x, uint32_t& mine, uint32_t other) -> bool {
+            const uint32_t n = mine;
+            if (n >= T) return false;
+            const uint32_t item = 2 * n - 1, st = item % S::kStages, par = (item / S::kStages) & 1u;
+            if (!mbar_test_wait(s_free(x), (n - 1) & 1u) || !mbar_test_wait(kv_full(st), par)) return false;
+            tc_fence_after();
+            issue_qk(x, stage_smem(st), no_probe);
+            commit(s_full(x));
+            if (other > n) commit(kv_empty(st));  // the other Q tile's QK(n) went out earlier: K(n) is done with
+            mine = n + 1;
+            return true;
+          };
+          auto try_pv = [&](int x, uint32_t& mine, uint32_t other) -> bool {
+            const uint32_t m = mine;
+            if (m >= T) return false;
+            const uint32_t item = (m + 1 < T) ? 2 * m + 2 : 2 * m + 1, st = item % S::kStages, par = (item / S::kStages) & 1u;
+            if (!mbar_test_wait(p_ready(x), m & 1u) || !mbar_test_wait(kv_full(st), par)) return false;
+            tc_fence_after();
+            issue_pv(x, stage_smem(st), m != 0, no_probe);
+            commit(o_done(x));
+            if (other > m) commit(kv_empty(st));
+            mine = m + 1;
+            return true;
+          };
+          if (p.issue_mode == 3) {
+            // PV first: P_X has a single buffer, so PV_X(t) has to be out of the way by the time the softmax of tile
+            // t+1 wants to store -- a tighter deadline than QK_X(t+2)'s, which has a whole softmax of slack
+            while (pv0 < T || pv1 < T) {
+              try_pv(0, pv0, pv1);
+              try_pv(1, pv1, pv0);
+              try_qk(0, qk0, qk1);
+              try_qk(1, qk1, qk0);
+            }
+          } else {
+            while (pv0 < T || pv1 < T) {
+              bool any = try_qk(0, qk0, qk1);
+              any |= try_qk(1, qk1, qk0);
+              any |= try_pv(0, pv0, pv1);
+              any |= try_pv(1, pv1, pv0);
+              if (!any && p.issue_mode == 2) __nanosleep(20);
+            }
+          }
+        } else if (DEC) {
           // P travels through shared memory (or spare TMEM columns), so S_X is free again as soon as the softmax warps hold it in
           // registers: QK_X(t+1) is issued ahead of PV_X(t) and the only per-tile dependency chain left is
           // the softmax itself. Per active tile t the groups go QK_A(t+1), PV_A(t), QK_B(t+1), PV_B(t); ring
@@ -671,15 +739,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
       trace_ev(p, tr, x, 3, t);
-      // the shared-memory P tile is read by PV_X(t-1) until o_done(x) completes its phase
-      if (DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+      // the P tile (shared memory / spare TMEM columns) is read by PV_X(t-1) until o_done(x) completes its phase.
+      // LS: all exponentials of the tile are computed and packed into registers first (64 registers replace the 128 of
+      // S as they are consumed) and the wait comes just before the burst of stores -- PV_X(t-1) has ~the whole softmax
+      // of tile t to finish instead of its first third, so the single P buffer stops serialising PV(t-1) and exp(t).
+      if (!LS && DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
       // ---- P = exp2(S*scale - m): over the first columns of S_X in TMEM, or into the P tile in smem ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 4 independent packed partial row sums
-      auto emit = [&](uint32_t(&r)[32], int c) {
-        uint32_t pk[16];
-        float pv[32];
+      constexpr int kPW = DT == kDtE4M3 ? 8 : 16;  // packed 32-bit words per 32 keys
+      auto compute = [&](uint32_t(&r)[32], uint32_t(&pk)[kPW]) {
+        float pv[DT == kDtE4M3 ? 32 : 1];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const uint64_t y = ffma2(f2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
@@ -693,24 +764,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             p1 = ex2(y1);
           }
           acc[i & 3] = fadd2(acc[i & 3], f2(p0, p1));
-          if (DT == kDtE4M3) {
+          if constexpr (DT == kDtE4M3) {
             pv[2 * i] = p0;
             pv[2 * i + 1] = p1;
           } else {
             pk[i] = pack2<DT>(p0, p1);
           }
         }
-        if (DT == kDtE4M3) {
+        if constexpr (DT == kDtE4M3) {
           // P -> e4m3, unscaled (the reference's fp8 semantics), 4 keys per 32-bit word
-          uint32_t p8[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) p8[i] = cvt_e4m3x4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) pk[i] = cvt_e4m3x4(pv[4 * i], pv[4 * i + 1], pv[4 * i + 2], pv[4 * i + 3]);
+        }
+      };
+      auto store = [&](const uint32_t(&pk)[kPW], int c) {
+        if constexpr (DT == kDtE4M3) {
           if (PS) {
 #pragma unroll
             for (int q = 0; q < 2; ++q)
-              sts128(p_row + ((((uint32_t)(c * 2 + q)) ^ p_sw) << 4), p8[4 * q], p8[4 * q + 1], p8[4 * q + 2], p8[4 * q + 3]);
+              sts128(p_row + ((((uint32_t)(c * 2 + q)) ^ p_sw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
           } else {
-            tmem_st_32x8(tP + (uint32_t)(c * 8), p8);
+            tmem_st_32x8(tP + (uint32_t)(c * 8), reinterpret_cast<const uint32_t(&)[8]>(pk));
           }
         } else if (PS) {
           // 32 keys = 64 bytes = four 16-byte chunks of this row in panel c/2 (64 keys per 128-byte row)
@@ -719,13 +793,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             sts128(p_row + (uint32_t)((c >> 1) * (kQTile * 128)) + ((((uint32_t)((c & 1) * 4 + q)) ^ p_sw) << 4),
                    pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         } else {
-          tmem_st_32x16(tP + (uint32_t)(c * 16), pk);
+          tmem_st_32x16(tP + (uint32_t)(c * 16), reinterpret_cast<const uint32_t(&)[16]>(pk));
         }
       };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
+      if constexpr (LS) {
+        uint32_t pk0[kPW], pk1[kPW], pk2[kPW], pk3[kPW];
+        compute(s0, pk0);
+        compute(s1, pk1);
+        compute(s2, pk2);
+        compute(s3, pk3);
+        trace_ev(p, tr, x, 7, t);
+        if (DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+        store(pk0, 0);
+        store(pk1, 1);
+        store(pk2, 2);
+        store(pk3, 3);
+      } else {
+        uint32_t pk[kPW];
+        compute(s0, pk);
+        store(pk, 0);
+        compute(s1, pk);
+        store(pk, 1);
+        compute(s2, pk);
+        store(pk, 2);
+        compute(s3, pk);
+        store(pk, 3);
+      }
       {
         float a0, a1, b0, b1;
         unf2(fadd2(acc[0], acc[1]), a0, a1);
@@ -802,13 +895,13 @@ template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE>
 static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const AttnParams& p, cudaStream_t st) {
   using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2, PS, CG>;
-  static bool attr_set[64] = {};
+  static std::atomic<bool> attr_set[64];  // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
   auto kern = attn_fwd_kernel<HD, DT, EMU, PS, CG, MASKED, TRACE>;
-  if (!attr_set[dev]) {
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set[dev] = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   const unsigned nq = (unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile));
   cudaLaunchConfig_t cfg = {};
@@ -833,7 +926,7 @@ static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
                          const AttnParams& p, cudaStream_t st) {
   if (p.trace != nullptr) {
     // the timeline build exists for the default dense bf16 hd-128 configurations only
-    if constexpr (HD == 128 && DT == kDtBF16 && EMU == 4) {
+    if constexpr (HD == 128 && DT == kDtBF16 && (EMU & 63) == 4) {
       if (p.mask == nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, false, true>(tq, tk, tv, p, st);
     }
   }
@@ -873,22 +966,35 @@ static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   return launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st);
 }
 
+// MMA issue policy of the kernels that keep P outside S (tuning knob, see the issuer loop)
+static int attn_issue_setting() {
+  static int v = attn_env("FDM_ATTN_ISSUE", 1);
+  return v;
+}
+
 // how many of every 32 exponentials run on the FMA pipe instead of MUFU (tuning knob; the default is
 // the measured optimum, FDM_ATTN_EMU overrides it for experiments)
 static int attn_emu_setting(int hd) {
-  static int v = -2;
-  if (v == -2) {
-    const char* e = getenv("FDM_ATTN_EMU");
-    v = e ? atoi(e) : -1;
-  }
+  static const int v = attn_env("FDM_ATTN_EMU", -1);
   if (v >= 0) return v;
   return hd == 128 ? 4 : 8;
+}
+
+// late store of P (see the softmax loop); FDM_ATTN_LS=0 restores the store-as-you-go order for experiments
+static bool attn_late_store() {
+  static const int v = attn_env("FDM_ATTN_LS", 1);
+  return v != 0;
 }
 
 template <int HD, int DT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, cudaStream_t st) {
   const int emu = attn_emu_setting(HD);
+  if (attn_late_store()) {
+    if (emu <= 0) return launch_attn_e<HD, DT, 64 + 0>(tq, tk, tv, p, st);
+    if (emu <= 4) return launch_attn_e<HD, DT, 64 + 4>(tq, tk, tv, p, st);
+    return launch_attn_e<HD, DT, 64 + 8>(tq, tk, tv, p, st);
+  }
   if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st);
   if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st);
   return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st);
@@ -966,6 +1072,7 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
     p.nbk = (int)((Sk + mask_bk - 1) / mask_bk);
   }
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.issue_mode = attn_issue_setting();
   p.trace = g_attn_trace;
   CUtensorMap tq, tk, tv;
   // batch stride of a single-batch tensor is irrelevant but must still be a legal stride

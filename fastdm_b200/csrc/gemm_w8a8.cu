@@ -18,6 +18,8 @@
 // Reference CUDA path being replaced: csrc/torch_bindings.cpp:24-160 -> csrc/gemm/*.cu (CUTLASS).
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "sm100.cuh"
 
 namespace fdm {
@@ -438,13 +440,13 @@ template <bool INT8, int BN, int ACT>
 static int launch_gemm_a(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                          cudaStream_t st) {
   using S = GemmSmem<BN>;
-  static bool attr_set[64] = {};
+  static std::atomic<bool> attr_set[64];  // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
-  if (!attr_set[dev]) {
+  if (!attr_set[dev].load(std::memory_order_acquire)) {
     FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN, ACT>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
-    attr_set[dev] = true;
+    attr_set[dev].store(true, std::memory_order_release);
   }
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -492,9 +494,9 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   if (bn == 128 && tiles_m * ((N + 127) / 128) < sms) bn = 64;
   if (N <= 64) bn = 64;
   else if (N <= 128 && bn > 128) bn = 128;
-  if (const char* e = getenv("FDM_GEMM_BN")) {  // experiments only
-    const int v = atoi(e);
-    if (v == 64 || v == 128 || v == 256) bn = v;
+  {  // experiments only (read once: thread-safe static initialisation, no getenv on the launch path)
+    static const int forced_bn = [] { const char* e = getenv("FDM_GEMM_BN"); return e ? atoi(e) : 0; }();
+    if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
   }
   const int64_t tiles_n = (N + bn - 1) / bn;
   FDM_REQUIRE(tiles_m * tiles_n < (1LL << 31), "gemm: too many tiles");

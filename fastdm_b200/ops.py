@@ -115,9 +115,6 @@ def _rms_norm(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float) -> to
     if weight is not None:
         if weight.numel() != cols:
             raise RuntimeError(f"fastdm_b200.rms_norm: weight has {weight.numel()} elements, last dim is {cols}")
-        if weight.dtype != x.dtype:
-            # reference torch backend: `input.to(scale.dtype) * scale` (kernel/torch/norm.py:21-23)
-            raise RuntimeError("fastdm_b200.rms_norm: weight dtype must equal input dtype")
         weight = weight.contiguous()
     # rows of the last dimension; accept any view whose leading dims collapse to one stride
     xc = x if x.is_contiguous() else x.contiguous()  # callers always pass contiguous (layer/transformer.py:275-290)
@@ -288,6 +285,9 @@ def _attn_fwd(out: torch.Tensor, query: torch.Tensor, key: torch.Tensor, value: 
         raise RuntimeError(f"fastdm_b200.{what}: q/k/v dtypes differ")
     if out.shape != query.shape or out.stride(2) != 1 or out.dtype != _attn_out_dtype(query.dtype):
         raise RuntimeError(f"fastdm_b200.{what}: out must be [batch, seq, heads*head_dim] with unit last stride")
+    if out.data_ptr() % 16 or out.stride(1) % 8 or (b > 1 and out.stride(0) % 8):
+        raise RuntimeError(f"fastdm_b200.{what}: out must be 16-byte aligned with token / batch strides that are "
+                           f"multiples of 8 elements (got data_ptr % 16 = {out.data_ptr() % 16}, strides {out.stride()})")
     ts = []
     for t in (query, key, value):
         # last-dim slices of a fused qkv projection are legal (layer/transformer.py:269,300)
@@ -297,11 +297,19 @@ def _attn_fwd(out: torch.Tensor, query: torch.Tensor, key: torch.Tensor, value: 
         ts.append(t)
     q, k, v = ts
     if block_mask is not None:
-        block_mask = block_mask.to(torch.int8).contiguous()
+        block_mask = block_mask.to(torch.int8)
         nbq, nbk = -(-sq // mask_bq), -(-sk // mask_bk)
-        if tuple(block_mask.shape) != (b, num_heads, nbq, nbk):
-            raise RuntimeError(f"fastdm_b200.{what}: sparse_mask must be {(b, num_heads, nbq, nbk)}, "
-                               f"got {tuple(block_mask.shape)}")
+        mq, mk = block_mask.shape[-2:] if block_mask.ndim == 4 else (-1, -1)
+        if block_mask.ndim != 4 or tuple(block_mask.shape[:2]) != (b, num_heads) or mq not in (sq // mask_bq, nbq) \
+                or mk not in (sk // mask_bk, nbk):
+            raise RuntimeError(f"fastdm_b200.{what}: sparse_mask must be {(b, num_heads, nbq, nbk)} (or floor-sized: "
+                               f"{(b, num_heads, sq // mask_bq, sk // mask_bk)}), got {tuple(block_mask.shape)}")
+        if (mq, mk) != (nbq, nbk):
+            # the reference's mask builders emit floor-sized masks (sparse/xsparse.py gen_log_mask_shrinked: S // block)
+            # and its wrapper pads q/k/v and pads the mask with ones (kernel/cuda/attention.py:118-133): the ragged
+            # trailing query / key blocks are computed
+            block_mask = torch.nn.functional.pad(block_mask, (0, nbk - mk, 0, nbq - mq), value=1)
+        block_mask = block_mask.contiguous()
     with torch.cuda.device(query.device):
         rc = _lib.load().fdm_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(block_mask),
                                       b, sq, sk, num_heads, head_dim,
@@ -340,7 +348,6 @@ def _qk_norm_rope(buf: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[to
     tokens, width = buf.shape
     if q_offset + q_heads * head_size > width or k_offset + k_heads * head_size > width:
         raise RuntimeError(f"fastdm_b200.{what}: q/k column ranges exceed the buffer width")
-    wn = head_size * (1 if not across_heads else 1)
     for w, hn in ((wq, q_heads), (wk, k_heads)):
         if w is not None:
             need = head_size * hn if across_heads else head_size
@@ -460,7 +467,14 @@ def ulysses_unpack_heads(x: torch.Tensor, num_heads: int, head_dim: int, n_seg: 
 # Public op API -- same names and signatures as fastdm/kernel/operators_set.py (reference)
 # ================================================================================================
 def rms_norm(input: torch.Tensor, scale: Optional[torch.Tensor], eps: float) -> torch.Tensor:
-    """operators_set.py:9-21; numerics of kernel/torch/norm.py:5-27."""
+    """operators_set.py:9-21; numerics of kernel/torch/norm.py:5-27.
+
+    A weight of another dtype than the input (not used on the DiT hot path): the reference promotes
+    (`input.to(scale.dtype) * scale`, norm.py:21-23) and returns the weight's dtype. Here the kernel runs in the
+    input dtype with the weight cast to it and the result is returned in the weight's dtype -- same dtype contract,
+    values within one rounding of the input dtype."""
+    if scale is not None and scale.dtype != input.dtype:
+        return torch.ops.fastdm_b200.rms_norm(input, scale.to(input.dtype), eps).to(scale.dtype)
     return torch.ops.fastdm_b200.rms_norm(input, scale, eps)
 
 

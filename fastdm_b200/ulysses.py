@@ -129,12 +129,18 @@ class UlyssesAttention:
         H, hd, P = self.H, self.hd, self.P
         d = H * hd
         dp = d // P
+        if len(project) != 3:
+            raise ValueError("qkv_projection_overlapped takes the three thunks of q, k and v")
         cur = torch.cuda.current_stream()
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream()
         recvs, events = [], []
         for thunk in project:
             x = thunk()                                           # [S/P, d] on the compute stream
+            if x.ndim != 2 or x.shape[1] != d:
+                # [B*S/P, d] with B > 1 would be exchanged (and attended to) as one long sequence
+                raise NotImplementedError(f"Ulysses: projections must be one sequence's [S/P, {d}] shard (batch 1), "
+                                          f"got {tuple(x.shape)}")
             send = _pack(x, H, hd, P, 1)
             ready = torch.cuda.Event()
             ready.record(cur)

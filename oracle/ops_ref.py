@@ -58,6 +58,10 @@ def quantize_to_int8(input: torch.Tensor, symmetric: bool = True
 # arithmetic is written out (SURVEY.md 8(c) shim 3).
 def fp8_matmul(a, b, scale_a, scale_b, out_dtype, bias=None):
     assert b.shape[0] % 16 == 0 and b.shape[1] % 16 == 0
+    if a.is_cuda:
+        # on a GPU the reference's own call (matrixmul.py:33) runs as is: this is the "torch backend on the
+        # same B200" arm of bench.py's gpu_torch_baseline leg (cuBLASLt rowwise-scaled fp8 GEMM)
+        return torch._scaled_mm(a, b, scale_a, scale_b.T, bias, out_dtype=out_dtype)
     acc = a.float() @ b.float()
     out = acc * scale_a.reshape(-1, 1) * scale_b.reshape(1, -1)
     if bias is not None:

@@ -232,6 +232,72 @@ def test_flux_block_pair_full_size_vs_oracle(lib):
     print(f"C1 block-pair cosines: text {c1:.6f} image {c2:.6f} single {c3:.6f}")
 
 
+def test_wan_block_full_width_vs_oracle(lib):
+    """The headline workload's block at its real width: Wan2.2-A14B, d = 5120, 40 x 128 heads, ffn 13824, FP8, on 2304
+    video tokens + 512 text tokens -- enough for the CTA-pair attention kernel (Sk >= 1024), the BN = 256 GEMM tiles on
+    multi-wave persistent grids and the across-heads q/k-norm kernel at 5120 columns. Oracle: oracle/blocks_ref.py
+    (fastdm/model/wan.py:67-114) on the CPU."""
+    from fastdm_b200.blocks import WanTransformerBlock
+
+    dim, heads, hd, ffn, S, T = 5120, 40, 128, 13824, 2304, 512
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(1, S, dim, generator=g).to(BF)
+    enc = torch.randn(1, T, dim, generator=g).to(BF)
+    temb = torch.randn(1, 6, dim, generator=g).to(BF)
+    cos = torch.rand(1, S, 1, hd, generator=g)
+    sin = torch.rand(1, S, 1, hd, generator=g)
+    sd = B.wan_block_state_dict("blocks.0", dim, ffn, seed=52)
+    quant = torch.float8_e4m3fn
+    want = B.WanTransformerBlockRef(sd, "blocks.0", heads, hd, quant).forward(x, enc, temb, (cos, sin))
+    blk = WanTransformerBlock(to_dev(sd), "blocks.0", heads, hd, quant)
+    got = blk.forward(x.to(DEV), enc.to(DEV), temb.to(DEV), (cos.to(DEV), sin.to(DEV)))
+    c = check(got, want, "Wan block d=5120")
+    print(f"Wan full-width block cosine: {c:.6f}")
+
+
+def test_qwen_block_full_width_vs_oracle(lib):
+    """Qwen-Image block at its real width: d = 3072, 24 x 128 heads, INT8 (asymmetric per-token activations), 2304 image +
+    128 text tokens (fastdm/model/qwenimage.py:58-124)."""
+    from fastdm_b200.blocks import QwenImageTransformerBlock
+
+    dim, heads, hd, S, T = 3072, 24, 128, 2304, 128
+    g = torch.Generator().manual_seed(61)
+    img = torch.randn(1, S, dim, generator=g).to(BF)
+    txt = torch.randn(1, T, dim, generator=g).to(BF)
+    temb = torch.randn(1, dim, generator=g).to(BF)
+    rope = torch.rand(S + T, hd, generator=g).to(BF)
+    sd = B.qwen_block_state_dict("transformer_blocks.0", dim, hd, seed=62)
+    quant = torch.int8
+    enc_r, hid_r = B.QwenImageTransformerBlockRef(sd, "transformer_blocks.0", heads, hd, quant).forward(img, txt, temb, rope)
+    blk = QwenImageTransformerBlock(to_dev(sd), "transformer_blocks.0", heads, hd, quant)
+    enc, hid = blk.forward(img.to(DEV), txt.to(DEV), None, temb.to(DEV), rope.to(DEV))
+    c1 = check(enc, enc_r, "Qwen block d=3072 / text")
+    c2 = check(hid, hid_r, "Qwen block d=3072 / image")
+    print(f"Qwen full-width block cosines: text {c1:.6f} image {c2:.6f}")
+
+
+@pytest.mark.parametrize("dual", [True, False])
+def test_sd3_block_full_width_vs_oracle(lib, dual):
+    """SD3.5-medium block at its real width: d = 1536, 24 x 64 heads, FP8, batch 2 (CFG), 2304 image + 333 text tokens,
+    with and without the second (image-only) attention (fastdm/model/sd35.py:133-200)."""
+    from fastdm_b200.blocks import JointTransformerBlock
+
+    dim, heads, hd, S, T = 1536, 24, 64, 2304, 333
+    g = torch.Generator().manual_seed(71)
+    img = torch.randn(2, S, dim, generator=g).to(BF)
+    txt = torch.randn(2, T, dim, generator=g).to(BF)
+    temb = torch.randn(2, dim, generator=g).to(BF)
+    sd = B.sd3_block_state_dict("transformer_blocks.0", dim, hd, 72, False, dual)
+    quant = torch.float8_e4m3fn
+    enc_r, hid_r = B.JointTransformerBlockRef(sd, "transformer_blocks.0", heads, hd, quant, False, dual).forward(img, txt, temb)
+    blk = JointTransformerBlock(to_dev(sd), "transformer_blocks.0", heads, hd, quant, context_pre_only=False,
+                                use_dual_attention=dual)
+    enc, hid = blk.forward(img.to(DEV), txt.to(DEV), temb.to(DEV))
+    c1 = check(enc, enc_r, "SD3.5 block d=1536 / text")
+    c2 = check(hid, hid_r, "SD3.5 block d=1536 / image")
+    print(f"SD3.5 full-width block (dual={dual}) cosines: text {c1:.6f} image {c2:.6f}")
+
+
 @pytest.mark.parametrize("quant", [torch.float8_e4m3fn, torch.int8])
 def test_final_latent_cosine_after_n_steps(quant):
     """north_star: "a final-latent cosine after N steps is also reported". An 8-step flow-matching Euler loop

@@ -482,6 +482,28 @@ def test_sparse_attention_banded_mask_skips_tiles(ops, hd):
     assert float(y[:, 5 * bq:6 * bq, hd:].abs().max()) == 0.0
 
 
+def test_sparse_attention_floor_sized_mask_is_padded_with_ones(ops):
+    """The reference's mask builders emit floor-sized masks (xsparse.gen_log_mask_shrinked: S // block) and its
+    wrapper pads the mask with ones (kernel/cuda/attention.py:118-133): sequences that are not a multiple of the
+    block size (Wan 480p: 21*30*52 = 32760 tokens) must work, the ragged trailing blocks being computed."""
+    b, sq, sk, h, hd, bq, bk = 1, 1000, 1100, 2, 128, 128, 64
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(b, sq, h * hd, generator=g).to(BF)
+    k = torch.randn(b, sk, h * hd, generator=g).to(BF)
+    v = torch.randn(b, sk, h * hd, generator=g).to(BF)
+    small = (torch.rand(b, h, sq // bq, sk // bk, generator=g) < 0.5).to(torch.int8)
+    small[:, :, :, 0] = 1
+    full = torch.nn.functional.pad(small, (0, -(-sk // bk) - sk // bk, 0, -(-sq // bq) - sq // bq), value=1)
+    assert full.shape[-2:] == (8, 18) and small.shape[-2:] == (7, 17)
+    y = ops.sparse_scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), h, h, hd, scale=hd ** -0.5,
+                                                sparse_mask=small.to(DEV), block_q=bq, block_k=bk)
+    ref = attn_oracle(q, k, v, h, hd, hd ** -0.5, full, bq, bk)
+    assert (y.cpu().float() - ref.float()).abs().max().item() <= ATOL_ATTN
+    with pytest.raises(RuntimeError, match="sparse_mask must be"):
+        ops.sparse_scaled_dot_product_attention(q.to(DEV), k.to(DEV), v.to(DEV), h, h, hd, sparse_mask=small[..., :5].to(DEV),
+                                                block_q=bq, block_k=bk)
+
+
 def test_sparse_attention_all_ones_equals_dense(ops):
     # the reference's only sparse test: tests/test_sparge_attention.py:81 (mask = ones)
     torch.manual_seed(0)

@@ -20,11 +20,14 @@ tr = buf.cpu().view(4, 8, 64)
 pair = os.environ.get("FDM_ATTN_CG", "2") == "2"
 t0 = int(tr[0, 0, 0])
 for t in range(8, 20):
-    a = [int(tr[0, e, t]) - t0 for e in range(6)]
-    bb = [int(tr[1, e, t]) - t0 for e in range(6)]
-    line = (f"tile {t:2d} | softA waitS {a[0]:6d} Srdy {a[1]:6d} ld {a[2]-a[1]:4d} max {a[3]-a[2]:4d} exp {a[4]-a[3]:4d} st+arr {a[5]-a[4]:4d} -> {a[5]:6d}"
-            f" | softB waitS {bb[0]:6d} Srdy {bb[1]:6d} ld {bb[2]-bb[1]:4d} max {bb[3]-bb[2]:4d} exp {bb[4]-bb[3]:4d} st+arr {bb[5]-bb[4]:4d} -> {bb[5]:6d}")
-    if pair:
+    a = [int(tr[0, e, t]) - t0 for e in range(8)]
+    bb = [int(tr[1, e, t]) - t0 for e in range(8)]
+    # late-store kernels stamp event 7 when all exponentials are packed in registers (before the wait for the P buffer)
+    ca = f" (packed +{a[7]-a[3]:4d})" if int(tr[0, 7, t]) else ""
+    cb = f" (packed +{bb[7]-bb[3]:4d})" if int(tr[1, 7, t]) else ""
+    line = (f"tile {t:2d} | softA waitS {a[0]:6d} Srdy {a[1]:6d} ld {a[2]-a[1]:4d} max {a[3]-a[2]:4d} exp {a[4]-a[3]:4d}{ca} st+arr {a[5]-a[4]:4d} -> {a[5]:6d}"
+            f" | softB waitS {bb[0]:6d} Srdy {bb[1]:6d} ld {bb[2]-bb[1]:4d} max {bb[3]-bb[2]:4d} exp {bb[4]-bb[3]:4d}{cb} st+arr {bb[5]-bb[4]:4d} -> {bb[5]:6d}")
+    if pair and os.environ.get("FDM_ATTN_ISSUE", "1") == "0":
         for r, nm in ((2, "mmaA"), (3, "mmaB")):
             m = [int(tr[r, e, t]) - t0 for e in range(7)]
             if r == 2:

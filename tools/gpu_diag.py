@@ -172,7 +172,8 @@ def attn_perf():
         fl = 4.0 * b * h * sq * sk * hd
         qt, kt, vt = (t.view(b, -1, h, hd).transpose(1, 2) for t in (q, k, v))
         try:
-            ms_t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), iters=5, warm=2)
+            ms_t = float("nan") if os.environ.get("FDM_DIAG_NO_TORCH") else timeit(
+                lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), iters=5, warm=2)
         except Exception as e:  # noqa: BLE001
             ms_t = float("nan")
             print("   torch sdpa failed:", str(e)[:200])
