@@ -21,6 +21,7 @@ explicit flush is needed between timed iterations (config.l2).
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -35,6 +36,12 @@ import torch  # noqa: E402
 WAN = dict(frames=21, height=96, width=160, in_ch=16, text_len=512, text_dim=4096, heads=40, head_dim=128,
            ffn=13824, layers=40)
 FLUX = dict(img_tokens=8192, txt_tokens=512, heads=24, head_dim=128, double=19, single=38)
+# examples/profiling/qwenimg_profiling.py:14-19 (1024x2048 -> img_shapes (1, 64, 128)); prompt length 512
+QWEN = dict(grid=(1, 64, 128), txt_tokens=512, txt_dim=3584, heads=24, head_dim=128, layers=60)
+# fastdm/model/sd35.py:202-221: SD3.5-medium 1024x1024, batch 2 (CFG), 333 text tokens
+SD3 = dict(batch=2, latent=(16, 128, 128), txt_tokens=333, txt_dim=4096, pooled=2048, heads=24, head_dim=64, layers=24)
+# algorithmic TFLOP per step (2*M*N*K of every quantised linear + 4*B*H*Sq*Sk*hd of every attention)
+STEP_TFLOP = dict(wan=7291.0, flux=165.4, qwen=118.3 + 55.9, sd3=2 * (7.35 + 4.58))
 
 
 def peaks():
@@ -170,6 +177,9 @@ def run_reference(args, rank):
         return
     threads = os.cpu_count() or 1
     wl = args.workload if args.workload != "auto" else "wan"
+    if wl not in ("wan", "flux"):
+        emit(dict(impl="reference", unavailable=f"the CPU arm restates the Wan and FLUX blocks only (not {wl})"))
+        return
     arm = CpuArm(wl, args.cpu_tokens, threads)
     vals, sample = [], ""
     for i in range(args.warmup + args.steps):
@@ -192,6 +202,17 @@ def workload_config(wl, n):
                              "40 blocks, d=5120, 40x128 heads, ffn 13824), FP8 per-token x per-channel W8A8, bf16 attention, "
                              "random-init weights",
                     parallelism=f"ulysses-sp{n}" if n > 1 else "single-gpu", l2="per-step activations (>=0.8 GB each) exceed the 126 MB L2; no flush")
+    if wl == "qwen":
+        return dict(workload="Qwen-Image 20B MMDiT transformer forward, 1024x2048 (8192 image + 512 text tokens, 60 blocks, d=3072, "
+                             "24x128 heads), INT8 per-token (asymmetric) x per-channel W8A8, bf16 attention, random-init weights",
+                    parallelism=f"ulysses-sp{n}" if n > 1 else "single-gpu",
+                    l2="per-step activations (0.16 GB per [8704, 9216] qkv buffer) exceed the 126 MB L2; no flush")
+    if wl == "sd3":
+        return dict(workload="SD3.5-medium MMDiT transformer forward, 1024x1024, batch 2 (CFG) (4096 image + 333 text tokens, 24 "
+                             "blocks, 13 with dual attention, d=1536, 24x64 heads), FP8 W8A8, bf16 attention, random-init weights",
+                    parallelism="single-gpu" if n == 1 else f"replicas x{n}",
+                    l2="one step touches 2.2 GB of weights + activations, more than the 126 MB L2; no flush",
+                    launch="whole step replayed as one CUDA graph (fastdm_b200.graph.GraphedStep); --no-graph launches eagerly")
     return dict(workload="FLUX.1-dev full transformer forward, 1024x2048 (8192 image + 512 text tokens, 19 double + 38 single "
                          "blocks, d=3072, 24x128 heads), FP8 per-token x per-channel W8A8, bf16 attention, random-init weights",
                 parallelism="single-gpu" if n == 1 else f"replicas x{n}", l2="per-step activations (0.14 GB each) exceed the 126 MB L2; no flush",
@@ -228,6 +249,31 @@ def build_flux(device, double, single):
     return model, host
 
 
+def build_qwen(device, layers):
+    from fastdm_b200.models import QwenImageTransformer2DModelCore
+
+    model = QwenImageTransformer2DModelCore(num_layers=layers, quant_dtype=torch.int8, device=device, seed=0)
+    g = torch.Generator().manual_seed(1)
+    f, h, w = QWEN["grid"]
+    host = dict(latent=torch.rand(1, f * h * w, 64, generator=g).to(torch.bfloat16).pin_memory(),
+                prompt=torch.rand(1, QWEN["txt_tokens"], QWEN["txt_dim"], generator=g).to(torch.bfloat16).pin_memory(),
+                timestep=torch.tensor([0.5]).pin_memory())
+    return model, host
+
+
+def build_sd3(device, layers):
+    from fastdm_b200.models import SD3TransformerModelCore
+
+    model = SD3TransformerModelCore(num_layers=layers, device=device, seed=0)
+    g = torch.Generator().manual_seed(1)
+    bf, b = torch.bfloat16, SD3["batch"]
+    host = dict(latent=torch.randn(b, *SD3["latent"], generator=g).to(bf).pin_memory(),
+                prompt=torch.randn(b, SD3["txt_tokens"], SD3["txt_dim"], generator=g).to(bf).pin_memory(),
+                pooled=torch.randn(b, SD3["pooled"], generator=g).to(bf).pin_memory(),
+                timestep=torch.tensor([500.0] * b).to(bf).pin_memory())
+    return model, host
+
+
 def to_device(host, device):
     return {k: v.to(device, non_blocking=True) for k, v in host.items()}
 
@@ -235,6 +281,10 @@ def to_device(host, device):
 def step_fn(wl, model, ulysses):
     if wl == "wan":
         return lambda d: model.forward(d["latent"], d["timestep"], d["prompt"], ulysses=ulysses)[0]
+    if wl == "qwen":
+        return lambda d: model.forward(d["latent"], d["prompt"], d["timestep"], QWEN["grid"], ulysses=ulysses)[0]
+    if wl == "sd3":
+        return lambda d: model.forward(d["latent"], d["prompt"], d["pooled"], d["timestep"])[0]
     return lambda d: model.forward(d["latent"], d["prompt"], d["pooled"], d["timestep"], d["img_ids"], d["txt_ids"], d["guidance"])[0]
 
 
@@ -293,12 +343,17 @@ def attention_roofline(wl, world, device, pk):
     CUDA events on the launching stream, algorithmic flops 4*B*H*Sq*Sk*hd per launch."""
     from fastdm_b200 import ops
 
+    Bt = 1
     if wl == "wan":
         S = WAN["frames"] * (WAN["height"] // 2) * (WAN["width"] // 2)
         H, hd = WAN["heads"] // world, WAN["head_dim"]
+    elif wl == "qwen":
+        S, H, hd = math.prod(QWEN["grid"]) + QWEN["txt_tokens"], QWEN["heads"] // world, QWEN["head_dim"]
+    elif wl == "sd3":
+        Bt, S, H, hd = SD3["batch"], 4096 + SD3["txt_tokens"], SD3["heads"], SD3["head_dim"]
     else:
         S, H, hd = FLUX["img_tokens"] + FLUX["txt_tokens"], FLUX["heads"], FLUX["head_dim"]
-    qkv = torch.randn(1, S, 3 * H * hd, device=device, dtype=torch.bfloat16)
+    qkv = torch.randn(Bt, S, 3 * H * hd, device=device, dtype=torch.bfloat16)
     d = H * hd
     run = lambda: ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd)  # noqa: E731
     run()
@@ -311,7 +366,7 @@ def attention_roofline(wl, world, device, pk):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    flops = 4.0 * H * S * S * hd
+    flops = 4.0 * Bt * H * S * S * hd
     ach = flops / ms / 1e9
     # DRAM bytes per launch of this kernel from the committed `ncu --set full` capture: profiles/attn_traffic.json
     # (written from the .ncu-rep by tools/ncu_traffic.py; only the N=1 launch shapes were captured)
@@ -321,9 +376,9 @@ def attention_roofline(wl, world, device, pk):
             traffic = json.load(f).get(f"{wl}_n{world}", {}).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    return dict(bound="tensor", kernel="attn_fwd_kernel<128,bf16>", achieved=ach, peak=pk["bf16"], unit="TFLOP/s",
+    return dict(bound="tensor", kernel=f"attn_fwd_kernel<{hd},bf16>", shape=[Bt, S, S, H, hd], achieved=ach, peak=pk["bf16"], unit="TFLOP/s",
                 frac=ach / pk["bf16"], traffic=traffic, traffic_unit="bytes/launch (dram read+write, ncu --set full)",
-                algorithmic_bytes=4.0 * S * H * hd * 2, ms_per_launch=ms, flops_per_launch=flops,
+                algorithmic_bytes=4.0 * Bt * S * H * hd * 2, ms_per_launch=ms, flops_per_launch=flops,
                 peak_source=pk["src"] + ", bf16 burst (kernel timed alone)")
 
 
@@ -346,22 +401,32 @@ def gemm_roofline(wl, device, pk):
     CUDA events; outputs (>= 0.2 GB) exceed L2. Also the same call through torch._scaled_mm (cuBLASLt rowwise)."""
     from fastdm_b200 import ops
 
-    M, K, N = (80640, 5120, 13824) if wl == "wan" else (8704, 3072, 12288)
+    M, K, N = dict(wan=(80640, 5120, 13824), flux=(8704, 3072, 12288), qwen=(8192, 3072, 12288), sd3=(8192, 1536, 6144))[wl]
     g = torch.Generator(device=device).manual_seed(3)
-    a = torch.randn(M, K, device=device, generator=g).to(torch.float8_e4m3fn)
-    b = torch.randn(N, K, device=device, generator=g).to(torch.float8_e4m3fn).t()
     sa = torch.rand(M, 1, device=device) * 0.01
     sb = torch.rand(N, 1, device=device)
     bias = torch.randn(N, device=device).to(torch.bfloat16)
     out = torch.empty(M, N, device=device, dtype=torch.bfloat16)
     it = 5 if wl == "wan" else 30
+    fl = 2.0 * M * N * K
+    if wl == "qwen":   # INT8 W8A8 with the asymmetric-activation zero-point correction (QLinear int8 path)
+        a = torch.randint(-128, 128, (M, K), device=device, generator=g).to(torch.int8)
+        b = torch.randint(-128, 128, (N, K), device=device, generator=g).to(torch.int8).t()
+        adj = b.to(torch.int32).sum(dim=0, keepdim=True, dtype=torch.int32)
+        azp = torch.randint(-128, 127, (M, 1), device=device).to(torch.int32)
+        ms = _cuda_ms(lambda: ops.int8_matmul(a, b, sa, sb, torch.bfloat16, adj, azp, bias, out=out), it, 2)
+        tf = fl / ms / 1e9
+        return dict(kernel="gemm_w8a8_kernel<int8>", shape=[M, K, N], ms=ms, tflops=tf, peak=2 * pk["bf16"], frac=tf / (2 * pk["bf16"]),
+                    peak_source="2 x measured bf16 burst (" + pk["src"] + "); nominal dense int8 4500", frac_of_nominal=tf / 4500.0,
+                    note="the reference torch backend computes int8 GEMMs as fp32 matmuls (kernel/torch/matrixmul.py:67); no library int8 arm timed")
+    a = torch.randn(M, K, device=device, generator=g).to(torch.float8_e4m3fn)
+    b = torch.randn(N, K, device=device, generator=g).to(torch.float8_e4m3fn).t()
     ms = _cuda_ms(lambda: ops.fp8_matmul(a, b, sa, sb, torch.bfloat16, bias, out=out), it, 2)
     try:
         ms_t = _cuda_ms(lambda: torch._scaled_mm(a, b, sa, sb.t(), bias, out_dtype=torch.bfloat16), it, 2)
     except Exception as e:  # noqa: BLE001
         print("bench: torch._scaled_mm failed:", str(e)[:200], file=sys.stderr)
         ms_t = None
-    fl = 2.0 * M * N * K
     tf = fl / ms / 1e9
     return dict(kernel="gemm_w8a8_kernel<fp8>", shape=[M, K, N], ms=ms, tflops=tf, peak=2 * pk["bf16"], frac=tf / (2 * pk["bf16"]),
                 peak_source="2 x measured bf16 burst (" + pk["src"] + "); nominal dense fp8 4500", frac_of_nominal=tf / 4500.0,
@@ -425,6 +490,81 @@ def gpu_torch_baseline(wl, device, ours_step_ms, roof, gemm):
                                       note="torch-backend time / our time on the same box: > 1 means we are faster"))
 
 
+def ulysses_parity(wl, model, dev_inputs, ulysses, device):
+    """gather(P-rank output) vs the 1-rank output of the SAME model on the first 2 blocks ("identical up to
+    attention-kernel tolerance" -- the per-head math is unchanged, only the order of the token shards' GEMM tiles is)."""
+    import torch.distributed as dist
+
+    attr = "blocks" if wl == "wan" else "transformer_blocks"
+    all_blocks = getattr(model, attr)
+    setattr(model, attr, all_blocks[:2])
+    try:
+        with torch.no_grad():
+            y1 = step_fn(wl, model, None)(dev_inputs).float()
+            yp = step_fn(wl, model, ulysses)(dev_inputs).float()
+    finally:
+        setattr(model, attr, all_blocks)
+    cos = torch.nn.functional.cosine_similarity(y1.flatten().double(), yp.flatten().double(), dim=0)
+    stats = torch.stack([cos.float(), -(y1 - yp).abs().max(), -y1.abs().max()])
+    dist.all_reduce(stats, op=dist.ReduceOp.MIN)   # worst rank
+    del y1, yp
+    torch.cuda.empty_cache()
+    return dict(cos=float(stats[0]), max_abs=float(-stats[1]), out_scale=float(-stats[2]), blocks=2, ranks=ulysses.P,
+                what="full forward (embed, 2 blocks, output projection, all-gather) sharded vs unsharded on every rank; worst rank")
+
+
+def secondary_workload(name, args, world, device, pk, rank):
+    """One more BASELINE configuration with the headline run's timing rules (W >= 3, CUDA events, max over ranks)."""
+    from fastdm_b200.ulysses import UlyssesAttention
+
+    build = dict(flux=lambda: build_flux(device, FLUX["double"], FLUX["single"]), sd3=lambda: build_sd3(device, SD3["layers"]),
+                 qwen=lambda: build_qwen(device, QWEN["layers"]))[name]
+    model, host = build()
+    uly = UlyssesAttention(QWEN["heads"], QWEN["head_dim"]) if (name == "qwen" and world > 1) else None
+    out = dict(config=workload_config(name, world))
+    fn = step_fn(name, model, uly)
+    dev_in = to_device(host, device)
+    if uly is not None:
+        out["ulysses_parity"] = ulysses_parity(name, model, dev_in, uly, device)
+    eager = fn
+    if name in ("flux", "sd3") and not args.no_graph:
+        from fastdm_b200.graph import GraphedStep
+        fn = GraphedStep(fn, dev_in)
+    out["ms_per_step"] = ms = timed_steps(fn, dev_in, 10, 3, world, device)
+    e2e, h2d, d2h = timed_e2e(fn, host, 5, world, device)
+    out.update(e2e_ms=e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, step_tflops_per_s=STEP_TFLOP[name] * 1e3 / ms)
+    if uly is not None:
+        uly.stub_comm = True
+        stub = timed_steps(fn, dev_in, 3, 1, world, device)
+        uly.stub_comm = False
+        out.update(a2a_exposed_ms=ms - stub, ms_per_step_comm_stubbed=stub)
+    if world == 1:
+        from fastdm_b200 import _lib
+        c0 = _lib.launch_count
+        eager(dev_in)
+        torch.cuda.synchronize()
+        out["gpu_launches"] = _lib.launch_count - c0
+        roof = attention_roofline(name, 1, device, pk)
+        out["attention_tflops"] = roof["achieved"]
+        out["attention_frac_of_bf16_burst"] = roof["frac"]
+        out["gemm"] = gemm_roofline(name, device, pk)
+        if name == "flux":
+            if not args.no_torch_baseline:
+                out["gpu_torch_baseline"] = gpu_torch_baseline("flux", device, ms, roof, out["gemm"])
+            # the same model at 1024x1024 (4096 image + 512 text tokens), the "FLUX 1024^2" of BASELINE.json's metric line
+            sq = {k: v for k, v in host.items()}
+            sq["latent"] = host["latent"][:, :4096].contiguous().pin_memory()
+            sq["img_ids"] = host["img_ids"][:4096].contiguous().pin_memory()
+            sfn = step_fn("flux", model, None)
+            if not args.no_graph:
+                from fastdm_b200.graph import GraphedStep
+                sfn = GraphedStep(sfn, to_device(sq, device))
+            out["ms_per_step_1024x1024"] = timed_steps(sfn, to_device(sq, device), 10, 3, 1, device)
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
 _JSON_FD = None
 
 
@@ -455,11 +595,14 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "wan", "flux"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "wan", "flux", "qwen", "sd3"],
+                    help="auto = wan as the headline plus the other BASELINE configurations as secondary entries")
     ap.add_argument("--layers", type=int, default=0, help="debug: fewer blocks (the JSON line then says so and is not a valid result)")
     ap.add_argument("--cpu-tokens", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flux", action="store_true", help="skip the secondary FLUX numbers at N=1")
+    ap.add_argument("--no-sd3", action="store_true", help="skip the secondary SD3.5 numbers at N=1")
+    ap.add_argument("--no-qwen", action="store_true", help="skip the secondary Qwen-Image numbers (timed at every N)")
     ap.add_argument("--no-sparse", action="store_true", help="skip the radial-sparse Wan variant at N=1")
     ap.add_argument("--no-graph", action="store_true", help="launch the FLUX step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true")
@@ -488,37 +631,49 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     wl = "wan" if args.workload == "auto" else args.workload
-    if wl == "flux" and world > 1:
-        pass  # replicas: every rank runs the same step, no collective (FLUX stays single-GPU)
     pk = peaks()
     _lib.load()
+    sequence_parallel = wl in ("wan", "qwen")   # FLUX / SD3.5 stay single-GPU: N ranks = N independent replicas
 
+    ulysses = None
     if wl == "wan":
-        layers = args.layers or WAN["layers"]
-        model, host = build_wan(device, layers)
-        ulysses = UlyssesAttention(WAN["heads"], WAN["head_dim"]) if world > 1 else None
+        model, host = build_wan(device, args.layers or WAN["layers"])
+        if world > 1:
+            ulysses = UlyssesAttention(WAN["heads"], WAN["head_dim"])
+    elif wl == "qwen":
+        model, host = build_qwen(device, args.layers or QWEN["layers"])
+        if world > 1:
+            ulysses = UlyssesAttention(QWEN["heads"], QWEN["head_dim"])
+    elif wl == "sd3":
+        model, host = build_sd3(device, args.layers or SD3["layers"])
     else:
-        layers = args.layers or (FLUX["double"] + FLUX["single"])
         model, host = build_flux(device, args.layers or FLUX["double"], args.layers or FLUX["single"])
-        ulysses = None
     fn0 = step_fn(wl, model, ulysses)
-    if ulysses is not None and args.no_overlap:
+    if wl == "wan" and ulysses is not None and args.no_overlap:
         fn = lambda d: model.forward(d["latent"], d["timestep"], d["prompt"], ulysses=ulysses, overlap=False)[0]  # noqa: E731
     else:
         fn = fn0
     dev_inputs = to_device(host, device)
     torch.cuda.synchronize()
-    if wl == "flux" and not args.no_graph:
+    extra = {}
+    if ulysses is not None:
+        # sharded == unsharded, checked on the device before anything is timed (2 blocks of the same model)
+        extra["ulysses_parity"] = ulysses_parity(wl, model, dev_inputs, ulysses, device)
+    if wl in ("flux", "sd3") and not args.no_graph:
         from fastdm_b200.graph import GraphedStep
-        fn = GraphedStep(fn, dev_inputs)   # ~1300 launches per step: replayed as one CUDA graph
+        fn = GraphedStep(fn, dev_inputs)   # 700-1300 short launches per step: replayed as one CUDA graph
 
     with ClockSampler(local_rank) as clocks:
         c0 = _lib.launch_count
         ms = timed_steps(fn, dev_inputs, args.steps, args.warmup, world, device)
         launches = (_lib.launch_count - c0) // (args.steps + args.warmup)
+    if launches == 0:   # graph replay: the library is not entered; count the launches of one eager step
+        c0 = _lib.launch_count
+        fn0(dev_inputs)
+        torch.cuda.synchronize()
+        launches = _lib.launch_count - c0
     e2e_ms, h2d, d2h = timed_e2e(fn, host, max(1, min(args.steps, 3)), world, device)
 
-    extra = {}
     if ulysses is not None:
         # exposed all-to-all time = step time - step time with the exchange replaced by a local copy
         ulysses.stub_comm = True
@@ -526,13 +681,14 @@ def main():
         ulysses.stub_comm = False
         extra["a2a_exposed_ms"] = ms - ms_stub
         extra["ms_per_step_comm_stubbed"] = ms_stub
-    roof = attention_roofline(wl, world, device, pk)
+    roof = attention_roofline(wl, world if sequence_parallel else 1, device, pk)
     if rank == 0 and world == 1:
         extra["gemm"] = gemm_roofline(wl, device, pk)
-        if not args.no_torch_baseline and not args.layers:
+        if not args.no_torch_baseline and not args.layers and wl in ("wan", "flux"):
             extra["gpu_torch_baseline"] = gpu_torch_baseline(wl, device, ms, roof, extra["gemm"])
 
-    if rank == 0 and wl == "wan" and world == 1 and not args.no_sparse and not args.layers:
+    secondary = wl == "wan" and args.workload == "auto" and not args.layers
+    if rank == 0 and secondary and world == 1 and not args.no_sparse:
         # BASELINE configs[4] "dense vs Sparge sparse attention": the same step with the reference's radial block
         # mask (examples/sparse/radial_attn_wan.json: block 64, decay 0.3, first layer dense) on self-attention
         from fastdm_b200.sparse import radial_block_mask, sparge_mask_convert
@@ -546,31 +702,17 @@ def main():
                                    "dense_layers 1, all steps sparse", block_sparsity=1.0 - conv.float().mean().item(),
                                    speedup_vs_dense=ms / sms)
         del smask, m64, conv
-    if rank == 0 and wl == "wan" and world == 1 and not args.no_flux and not args.layers:
-        del model
+    if secondary:
+        # the other BASELINE configurations, reported next to the headline one (same timing rules). FLUX and SD3.5 are
+        # single-GPU models (N = 1 only); Qwen-Image is sequence-parallel and is timed at every N.
+        del model, fn, fn0
         torch.cuda.empty_cache()
-        fmodel, fhost = build_flux(device, FLUX["double"], FLUX["single"])
-        ffn = step_fn("flux", fmodel, None)
-        if not args.no_graph:
-            from fastdm_b200.graph import GraphedStep
-            ffn = GraphedStep(ffn, to_device(fhost, device))
-        fms = timed_steps(ffn, to_device(fhost, device), 10, 3, 1, device)
-        fe2e, fh2d, fd2h = timed_e2e(ffn, fhost, 5, 1, device)
-        froof = attention_roofline("flux", 1, device, pk)
-        extra["flux"] = dict(config=workload_config("flux", 1), ms_per_step=fms, e2e_ms=fe2e, h2d_bytes_per_step=fh2d,
-                             d2h_bytes_per_step=fd2h, attention_tflops=froof["achieved"],
-                             step_tflops=165.4e3 / fms, gemm=gemm_roofline("flux", device, pk))
-        if not args.no_torch_baseline:
-            extra["flux"]["gpu_torch_baseline"] = gpu_torch_baseline("flux", device, fms, froof, extra["flux"]["gemm"])
-        # the same model at 1024x1024 (4096 image + 512 text tokens), the "FLUX 1024^2" of BASELINE.json's metric line
-        sq = {k: v for k, v in fhost.items()}
-        sq["latent"] = fhost["latent"][:, :4096].contiguous().pin_memory()
-        sq["img_ids"] = fhost["img_ids"][:4096].contiguous().pin_memory()
-        sfn = step_fn("flux", fmodel, None)
-        if not args.no_graph:
-            sfn = GraphedStep(sfn, to_device(sq, device))
-        extra["flux"]["ms_per_step_1024x1024"] = timed_steps(sfn, to_device(sq, device), 10, 3, 1, device)
-        del fmodel
+        for name in ("flux", "sd3", "qwen"):
+            if getattr(args, f"no_{name}") or (world > 1 and name != "qwen"):
+                continue
+            res = secondary_workload(name, args, world, device, pk, rank)
+            if rank == 0:
+                extra[name] = res
 
     if rank != 0:
         if world > 1:
@@ -578,17 +720,19 @@ def main():
             dist.destroy_process_group()
         return
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and wl in ("wan", "flux"):
         threads = os.cpu_count() or 1
         v, sample = CpuArm(wl, args.cpu_tokens, threads).step()
         cpu = dict(value=v, unit="ms", cores=threads, kind="port", sample=sample)
     cfg = workload_config(wl, world)
     if args.layers:
         cfg["INVALID_debug_layers"] = args.layers
-    step_tflop = 7291.0 if wl == "wan" else 165.4
+    step_tflop = STEP_TFLOP[wl]
+    dtype = "int8 GEMM (s32 accumulate), bf16 attention (f32 accumulate)" if wl == "qwen" else \
+        "fp8_e4m3 GEMM (f32 accumulate), bf16 attention (f32 accumulate)"
     line = dict(metric="dit_denoise_step_ms", value=ms, unit="ms", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms, higher_is_better=False, scaling="strong" if wl == "wan" else "weak", vs_baseline=None,
-                dtype="fp8_e4m3 GEMM (f32 accumulate), bf16 attention (f32 accumulate)", data="synthetic", config=cfg,
+                ms_per_step=ms, higher_is_better=False, scaling="strong" if sequence_parallel else "weak", vs_baseline=None,
+                dtype=dtype, data="synthetic", config=cfg,
                 clocks=clocks.summary(),
                 e2e=dict(value=e2e_ms, unit="ms", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
                 gpu_launches=launches, roofline=roof, cpu_baseline=cpu,

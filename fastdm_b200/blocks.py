@@ -112,6 +112,14 @@ class _JointDiTBlock:
             load_linear(sd, [f"{p}.{ff_txt}.net.0.proj"], q, dv), load_linear(sd, [f"{p}.{ff_txt}.net.2"], q, dv))
         self.scale = self.hd ** -0.5
 
+    def _modulated(self, x, scale, shift, eps):
+        """LayerNorm(x) * (1 + scale) + shift in the model dtype (the fused kernel with the quantisation switched off):
+        the tensor TeaCache thresholds on (fastdm/caching/xcaching.py:164-185)."""
+        B, S, d = x.shape
+        a, c = _mod(scale, shift)
+        y = ops.layernorm_modulate_quant(x.reshape(B * S, d), a, c, S, None, eps)[3]
+        return y.view(B, S, d)
+
     def _forward_joint(self, hidden_states, encoder_hidden_states, img_mod, txt_mod, image_rotary_emb,
                        dual_mod=None, context_pre_only=False, eps1=None, ulysses=None, rope_pos=None):
         """img_mod / txt_mod: (shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp), each [B, dim].
@@ -220,6 +228,11 @@ class FluxTransformerBlock(_JointDiTBlock):
         return self._forward_joint(hidden_states, encoder_hidden_states, emb.chunk(6, dim=1), cemb.chunk(6, dim=1),
                                    image_rotary_emb)
 
+    def cache_indicator(self, hidden_states, encoder_hidden_states, temb):
+        """TeaCache: `transformer_blocks[0].norm1.forward(inp, emb=temb)[0]` (xcaching.py:181-183, AdaLayerNormZero)."""
+        shift_msa, scale_msa = self.norm1_linear.forward(F.silu(temb)).chunk(6, dim=1)[:2]
+        return self._modulated(hidden_states, scale_msa, shift_msa, self.eps)
+
 
 class QwenImageTransformerBlock(_JointDiTBlock):
     """fastdm/model/qwenimage.py:16-124 (+ Attention.forward_qwen, layer/transformer.py:319-391):
@@ -246,6 +259,11 @@ class QwenImageTransformerBlock(_JointDiTBlock):
             txt = self.txt_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)
         return self._forward_joint(hidden_states, encoder_hidden_states, img, txt, image_rotary_emb,
                                    ulysses=ulysses, rope_pos=rope_pos)
+
+    def cache_indicator(self, hidden_states, encoder_hidden_states, temb):
+        """TeaCache on Qwen-Image thresholds on the modulated TEXT stream of block 0 (xcaching.py:169-180)."""
+        shift, scale = self.txt_mod_proj.forward(F.silu(temb)).chunk(6, dim=-1)[:2]
+        return self._modulated(encoder_hidden_states, scale, shift, self.eps)
 
 
 class JointTransformerBlock(_JointDiTBlock):
@@ -284,6 +302,12 @@ class JointTransformerBlock(_JointDiTBlock):
             txt_mod = cemb.chunk(6, dim=1)
         return self._forward_joint(hidden_states, encoder_hidden_states, img_mod, txt_mod, None, dual_mod=dual,
                                    context_pre_only=self.context_pre_only, eps1=eps1)
+
+    def cache_indicator(self, hidden_states, encoder_hidden_states, temb):
+        """TeaCache: first output of norm1 (AdaLayerNormZero, or SD35AdaLayerNormZeroX on the dual-attention blocks)."""
+        emb = self.norm1_linear.forward(F.silu(temb).to(hidden_states.dtype))
+        shift_msa, scale_msa = emb.chunk(9 if self.use_dual_attention else 6, dim=1)[:2]
+        return self._modulated(hidden_states, scale_msa, shift_msa, 1e-5 if self.use_dual_attention else 1e-6)
 
 
 class FluxSingleTransformerBlock:

@@ -218,6 +218,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto trace_ev = [&](const AttnParams& pp, bool on, int role, int ev, uint32_t tile) { trace_ev_t<TRACE>(pp, on, role, ev, tile); };
   const int8_t* mask_bh = has_mask ? p.mask + ((int64_t)b * p.H + h) * p.nbq * p.nbk : nullptr;
 
+  // TRACE: CTA life-cycle stamps in trace[(3 * 8 + 7) * 64 + i]: 0 kernel entry, 1 set-up done, 2 epilogue start, 3 epilogue
+  // end, 4 kernel exit
+  const bool life = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0;
+  if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 0] = clock64();
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_k);
@@ -262,6 +266,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (CG == 2) cluster_sync();  // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 1] = clock64();
   auto tile_active = [&](int j) -> bool { return !has_mask || ((flags[j >> 3] >> (j & 7)) & 1) != 0; };
   auto next_active = [&](int j) {  // first active tile >= j, or n_kv_tiles
     if (!has_mask) return j;
@@ -452,7 +457,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             mine = m + 1;
             return true;
           };
-          if (p.issue_mode == 3) {
+          if (p.issue_mode == 4) {
+            // fixed order QK_A(t+1), QK_B(t+1), PV_A(t), PV_B(t): like the greedy order neither tile's QK waits for the
+            // other tile's softmax, but the two softmaxes stay a fixed ~512 cycles apart
+            while (pv1 < T) {
+              if (qk0 < T) while (!try_qk(0, qk0, qk1)) {}
+              if (qk1 < T) while (!try_qk(1, qk1, qk0)) {}
+              while (!try_pv(0, pv0, pv1)) {}
+              while (!try_pv(1, pv1, pv0)) {}
+            }
+          } else if (p.issue_mode == 3) {
             // PV first: P_X has a single buffer, so PV_X(t) has to be out of the way by the time the softmax of tile
             // t+1 wants to store -- a tighter deadline than QK_X(t+2)'s, which has a whole softmax of slack
             while (pv0 < T || pv1 < T) {
@@ -845,6 +859,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
 
     // ---- epilogue: O / l -> global ----
+    if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 2] = clock64();
     const bool row_ok = row < p.Sq;
     uint16_t* out_row = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ts + (int64_t)h * HD;
     if (t > 0) {
@@ -882,9 +897,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   }
 
+  if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 3] = clock64();
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync();  // neither CTA's shared memory / TMEM goes away while the pair is still working
+  if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 4] = clock64();
   if (warp == 9) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, 512);
@@ -968,7 +985,7 @@ static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 
 // MMA issue policy of the kernels that keep P outside S (tuning knob, see the issuer loop)
 static int attn_issue_setting() {
-  static int v = attn_env("FDM_ATTN_ISSUE", 1);
+  static int v = attn_env("FDM_ATTN_ISSUE", 0);
   return v;
 }
 
@@ -977,7 +994,7 @@ static int attn_issue_setting() {
 static int attn_emu_setting(int hd) {
   static const int v = attn_env("FDM_ATTN_EMU", -1);
   if (v >= 0) return v;
-  return hd == 128 ? 4 : 8;
+  return hd == 128 ? 4 : 12;
 }
 
 // late store of P (see the softmax loop); FDM_ATTN_LS=0 restores the store-as-you-go order for experiments
@@ -993,7 +1010,9 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   if (attn_late_store()) {
     if (emu <= 0) return launch_attn_e<HD, DT, 64 + 0>(tq, tk, tv, p, st);
     if (emu <= 4) return launch_attn_e<HD, DT, 64 + 4>(tq, tk, tv, p, st);
-    return launch_attn_e<HD, DT, 64 + 8>(tq, tk, tv, p, st);
+    if (emu <= 8) return launch_attn_e<HD, DT, 64 + 8>(tq, tk, tv, p, st);
+    if (emu <= 12) return launch_attn_e<HD, DT, 64 + 12>(tq, tk, tv, p, st);
+    return launch_attn_e<HD, DT, 64 + 16>(tq, tk, tv, p, st);
   }
   if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st);
   if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st);

@@ -7,6 +7,8 @@
 // The reference kernels (csrc/elmwise_ops.cu) read each row twice, use 8-byte loads and one CTA
 // per (token, head); arithmetic here follows the *torch backend* (fastdm/kernel/torch/*.py), which
 // is the parity oracle, not the reference CUDA formulas (SURVEY.md finding 0.6).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace fdm {
@@ -1297,6 +1299,73 @@ int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* 
   else LNQ_CALL(3);
 #undef LNQ_CALL
   FDM_LAUNCH_CHECK("layernorm_modulate_quant kernel launch");
+  return FDM_OK;
+}
+
+// ---- caching policies: relative L1 distance of two activations, reduced on the device ------------------
+// TeaCache / FBCache / DiCache (fastdm/caching/xcaching.py:214-215, 361-362, 479-480) evaluate
+// (a - b).abs().mean() / b.abs().mean() with five full-size torch kernels and two full-size temporaries per
+// step. Here: one pass over a and b, out[0] = sum |T(a - b)|, out[1] = sum |b| (T = rounding to the tensor
+// dtype, as the torch subtraction does); the caller turns the two sums into the reference's ratio.
+}  // extern "C"
+namespace fdm {
+template <typename T>
+__global__ void __launch_bounds__(256) rel_l1_kernel(const T* __restrict__ a, const T* __restrict__ b, int64_t n,
+                                                     float* __restrict__ out) {
+  float sd = 0.f, sb = 0.f;
+  const int64_t nvec = n / 8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float fa[8], fb[8];
+    unpack8<T>(ldg128_stream(a + i * 8), fa);
+    unpack8<T>(ldg128_stream(b + i * 8), fb);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sd += fabsf(round_to<T>(fa[j] - fb[j]));
+      sb += fabsf(fb[j]);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - nvec * 8)) {  // ragged tail
+    const float x = Elem<T>::to_f(a[nvec * 8 + threadIdx.x]), y = Elem<T>::to_f(b[nvec * 8 + threadIdx.x]);
+    sd += fabsf(round_to<T>(x - y));
+    sb += fabsf(y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  __shared__ float red[2][8];
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = sd;
+    red[1][threadIdx.x >> 5] = sb;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+    atomicAdd(out + threadIdx.x, t);
+  }
+}
+}  // namespace fdm
+extern "C" {
+
+int fdm_rel_l1_distance(const void* a, const void* b, int64_t n, int dtype, float* out2, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  FDM_REQUIRE(n >= 0 && out2, "rel_l1_distance: bad arguments");
+  FDM_REQUIRE(dtype == FDM_BF16 || dtype == FDM_F16, "rel_l1_distance: dtype must be bf16 or f16");
+  cudaStream_t st = (cudaStream_t)stream;
+  FDM_CUDA(cudaMemsetAsync(out2, 0, 2 * sizeof(float), st));
+  if (n == 0) return FDM_OK;
+  FDM_REQUIRE(a && b, "rel_l1_distance: null pointer");
+  FDM_REQUIRE((uintptr_t)a % 16 == 0 && (uintptr_t)b % 16 == 0, "rel_l1_distance: pointers must be 16-byte aligned");
+  const unsigned g = (unsigned)std::min<int64_t>((n / 8 + 255) / 256 + 1, (int64_t)num_sms() * 8);
+  if (dtype == FDM_BF16)
+    rel_l1_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n, out2);
+  else
+    rel_l1_kernel<__half><<<g, 256, 0, st>>>((const __half*)a, (const __half*)b, n, out2);
+  FDM_LAUNCH_CHECK("rel_l1_distance kernel launch");
   return FDM_OK;
 }
 

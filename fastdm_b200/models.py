@@ -22,6 +22,13 @@ from .blocks import (AdaLNTable, FluxSingleTransformerBlock, FluxTransformerBloc
 from .layers import QLinear, load_linear
 
 
+def _caching(model) -> bool:
+    """`model.cache` (a fastdm_b200.caching.AutoCache, set by the caller like the reference's `cache=` constructor
+    argument) is active: fastdm/model/flux.py:268-271."""
+    cache = getattr(model, "cache", None)
+    return cache is not None and cache.config.enable_caching
+
+
 # ---- small embedders (fastdm/layer/embeddings.py) ------------------------------------------------
 def get_timestep_embedding(timesteps, embedding_dim, flip_sin_to_cos=False, downscale_freq_shift=1.0, scale=1.0,
                            max_period=10000):
@@ -197,6 +204,12 @@ class FluxTransformer2DModelCore:
         if img_ids.ndim == 3:
             img_ids = img_ids[0]
         rope = flux_rope_table(torch.cat((txt_ids, img_ids), dim=0), self.axes_dims_rope, dt)    # flux.py:417-428
+        if _caching(self):                                                                       # flux.py:430-443
+            hidden_states = self.cache.apply_cache(
+                model_type="flux", hidden_states=hidden_states, encoder_hidden_states=encoder_hidden_states, temb=temb,
+                image_rotary_emb=rope, transformer_blocks=self.transformer_blocks,
+                single_transformer_blocks=self.single_transformer_blocks)
+            return (self._project_out(hidden_states, temb, dt),)
         use_table = self.use_adaln_table
         tables = self.adaln.compute(F.silu(temb)) if use_table else None
         for i, block in enumerate(self.transformer_blocks):                                      # flux.py:445-452
@@ -209,12 +222,15 @@ class FluxTransformer2DModelCore:
             hidden_states = block.forward(hidden_states, temb, rope,
                                           mod=self.adaln.chunks(tables, n_double + i, 3) if use_table else None)
         hidden_states = hidden_states[:, t:, ...]
+        return (self._project_out(hidden_states, temb, dt),)
+
+    def _project_out(self, hidden_states, temb, dt):
         # AdaLayerNormContinuous (normalization.py:90-128) + proj_out
         emb = self.norm_out_linear.forward(F.silu(temb).to(dt))
         scale, shift = torch.chunk(emb, 2, dim=1)
         hidden_states = F.layer_norm(hidden_states, (self.inner_dim,), None, None, 1e-6) * (1 + scale)[:, None, :] \
             + shift[:, None, :]
-        return (self.proj_out.forward(hidden_states),)
+        return self.proj_out.forward(hidden_states)
 
 
 # ---- Wan -------------------------------------------------------------------------------------------
@@ -301,9 +317,17 @@ class WanTransformer3DModelCore:
         if ulysses is not None and ulysses.P > 1:
             x = ulysses.shard_tokens(x, dim=1)
             pos0 = ulysses.rank * x.shape[1]
-        for i, block in enumerate(self.blocks):
-            mask = sparse_mask if (sparse_mask is not None and i >= dense_layers) else None
-            x = block.forward(x, enc, timestep_proj, rope, mask, ulysses=ulysses, pos0=pos0, overlap=overlap)
+        if _caching(self):                                                                       # wan.py:339-349
+            if ulysses is not None and ulysses.P > 1:
+                raise NotImplementedError("step caches are not combined with Ulysses sharding (the indicator would need an "
+                                          "all-reduce per step)")
+            x = self.cache.apply_cache(model_type="wan", hidden_states=x, encoder_hidden_states=enc, temb=timestep_proj,
+                                       image_rotary_emb=rope, transformer_blocks=self.blocks,
+                                       sparse_attn=(sparse_mask, dense_layers) if sparse_mask is not None else None)
+        else:
+            for i, block in enumerate(self.blocks):
+                mask = sparse_mask if (sparse_mask is not None and i >= dense_layers) else None
+                x = block.forward(x, enc, timestep_proj, rope, mask, ulysses=ulysses, pos0=pos0, overlap=overlap)
         y = self.project_out(x, temb)
         if ulysses is not None and ulysses.P > 1:
             y = ulysses.gather_tokens(y, dim=1)
@@ -407,10 +431,16 @@ class QwenImageTransformer2DModelCore:
             x = ulysses.shard_tokens(x, dim=1)
             enc = ulysses.shard_tokens(enc, dim=1)
             rope_pos = (ulysses.rank * enc.shape[1], T + ulysses.rank * x.shape[1])
-        tables = self.adaln.compute(F.silu(temb)) if self.use_adaln_table else None
-        for i, block in enumerate(self.transformer_blocks):                                       # :331-340
-            mod = (self.adaln.chunks(tables, 2 * i, 6), self.adaln.chunks(tables, 2 * i + 1, 6)) if tables is not None else None
-            enc, x = block.forward(x, enc, None, temb, rope, mod=mod, ulysses=ulysses, rope_pos=rope_pos)
+        if _caching(self):                                                                        # qwenimage.py:316-329
+            if ulysses is not None and ulysses.P > 1:
+                raise NotImplementedError("step caches are not combined with Ulysses sharding")
+            x = self.cache.apply_cache(model_type="qwenimage", hidden_states=x, encoder_hidden_states=enc, temb=temb,
+                                       image_rotary_emb=rope, transformer_blocks=self.transformer_blocks)
+        else:
+            tables = self.adaln.compute(F.silu(temb)) if self.use_adaln_table else None
+            for i, block in enumerate(self.transformer_blocks):                                   # :331-340
+                mod = (self.adaln.chunks(tables, 2 * i, 6), self.adaln.chunks(tables, 2 * i + 1, 6)) if tables is not None else None
+                enc, x = block.forward(x, enc, None, temb, rope, mod=mod, ulysses=ulysses, rope_pos=rope_pos)
         emb = self.norm_out_linear.forward(F.silu(temb).to(dt))                                   # AdaLayerNormContinuous
         scale, shift = torch.chunk(emb, 2, dim=1)
         x = F.layer_norm(x, (self.inner_dim,), None, None, 1e-6) * (1 + scale)[:, None, :] + shift[:, None, :]
@@ -502,8 +532,12 @@ class SD3TransformerModelCore:
             get_timestep_embedding(timestep, 256, flip_sin_to_cos=True, downscale_freq_shift=0).to(dt))
         temb = temb + self.text_embedder.forward(pooled_projections)                             # :381
         enc = self.context_embedder.forward(encoder_hidden_states)                               # :382
-        for block in self.transformer_blocks:                                                    # :394-400
-            enc, x = block.forward(x, enc, temb)
+        if _caching(self):                                                                       # sd35.py:383-393
+            x = self.cache.apply_cache(model_type="sd35", hidden_states=x, encoder_hidden_states=enc, temb=temb,
+                                       transformer_blocks=self.transformer_blocks)
+        else:
+            for block in self.transformer_blocks:                                                # :394-400
+                enc, x = block.forward(x, enc, temb)
         emb = self.norm_out_linear.forward(F.silu(temb).to(dt))
         scale, shift = torch.chunk(emb, 2, dim=1)
         x = F.layer_norm(x, (self.inner_dim,), None, None, 1e-6) * (1 + scale)[:, None, :] + shift[:, None, :]

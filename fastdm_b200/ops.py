@@ -463,6 +463,24 @@ def ulysses_unpack_heads(x: torch.Tensor, num_heads: int, head_dim: int, n_seg: 
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# step-cache indicator
+# ------------------------------------------------------------------------------------------------
+def rel_l1_sums(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """One pass over a and b -> fp32 device tensor [sum |T(a - b)|, sum |b|] (T = rounding to the tensor dtype):
+    the two reductions of `(a - b).abs().mean() / b.abs().mean()` (fastdm/caching/xcaching.py:214-215)."""
+    _cuda(a, "rel_l1_distance")
+    if a.shape != b.shape or a.dtype != b.dtype or a.device != b.device:
+        raise RuntimeError("fastdm_b200.rel_l1_distance: a and b must have the same shape, dtype and device")
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty(2, device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().fdm_rel_l1_distance(a.data_ptr(), b.data_ptr(), a.numel(), _dt(a, "rel_l1_distance"),
+                                             out.data_ptr(), _stream(a))
+    _lib.check(rc, "rel_l1_distance")
+    return out
+
+
 # ================================================================================================
 # Public op API -- same names and signatures as fastdm/kernel/operators_set.py (reference)
 # ================================================================================================

@@ -232,6 +232,15 @@ int fdm_ulysses_unpack_heads(const void* src, void* dst, int64_t S_local, int H,
                              int n_seg, int64_t dst_token_stride, int64_t dst_seg_stride,
                              int elem_size, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Step-cache indicator: the relative L1 distance TeaCache / FBCache / DiCache threshold on,
+ *   (a - b).abs().mean() / b.abs().mean()        fastdm/caching/xcaching.py:214-215, 361-362, 479-480
+ * as ONE pass over a and b instead of five full-size torch kernels: out2[0] = sum |T(a - b)| (T = rounding to
+ * the tensor dtype, as the reference's bf16 subtraction does), out2[1] = sum |b|, both fp32, device memory
+ * (zeroed by the call). n elements, contiguous, 16-byte aligned; dtype FDM_BF16 or FDM_F16.
+ * ------------------------------------------------------------------------------------------- */
+int fdm_rel_l1_distance(const void* a, const void* b, int64_t n, int dtype, float* out2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

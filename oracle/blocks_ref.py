@@ -457,3 +457,46 @@ def wan_block_state_dict(prefix, dim, ffn_dim, seed, dtype=torch.bfloat16):
     _lin(sd, f"{p}.ffn.net.2", dim, ffn_dim, g)
     sd[f"{p}.scale_shift_table"] = (torch.randn(1, 6, dim, generator=g) / dim ** 0.5).to(dtype)
     return sd
+
+
+# ---- whole-model synthetic state dicts (reduced width; tests/golden/model_*.pt regenerate them from the seed) --------
+def flux_model_state_dict(cfg, seed, dtype=torch.bfloat16):
+    """Keys of fastdm/model/flux.py:274-328 for a FluxTransformer2DModelCore(**cfg)."""
+    g = torch.Generator().manual_seed(seed)
+    d, hd = cfg["num_attention_heads"] * cfg["attention_head_dim"], cfg["attention_head_dim"]
+    sd = {}
+    for n in ("timestep_embedder", "guidance_embedder"):
+        _lin(sd, f"time_text_embed.{n}.linear_1", d, 256, g)
+        _lin(sd, f"time_text_embed.{n}.linear_2", d, d, g)
+    _lin(sd, "time_text_embed.text_embedder.linear_1", d, cfg["pooled_projection_dim"], g)
+    _lin(sd, "time_text_embed.text_embedder.linear_2", d, d, g)
+    _lin(sd, "context_embedder", d, cfg["joint_attention_dim"], g)
+    _lin(sd, "x_embedder", d, cfg["in_channels"], g)
+    _lin(sd, "norm_out.linear", 2 * d, d, g)
+    _lin(sd, "proj_out", cfg["out_channels"], d, g)
+    for i in range(cfg["num_layers"]):
+        sd.update(flux_double_state_dict(f"transformer_blocks.{i}", d, hd, seed=seed * 100 + i, dtype=dtype))
+    for i in range(cfg["num_single_layers"]):
+        sd.update(flux_single_state_dict(f"single_transformer_blocks.{i}", d, hd, seed=seed * 100 + 50 + i, dtype=dtype))
+    return sd
+
+
+def wan_model_state_dict(cfg, seed, dtype=torch.bfloat16):
+    """Keys of fastdm/model/wan.py:216-281 for a WanTransformer3DModelCore(**cfg) (text-to-video)."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    d = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    ps = cfg.get("patch_size", (1, 2, 2))
+    sd = {}
+    sd["patch_embedding.weight"] = (torch.randn(d, cfg["in_channels"], *ps, generator=g) * 0.05).to(dtype)
+    sd["patch_embedding.bias"] = (torch.randn(d, generator=g) * 0.02).to(dtype)
+    _lin(sd, "condition_embedder.time_embedder.linear_1", d, cfg["freq_dim"], g)
+    _lin(sd, "condition_embedder.time_embedder.linear_2", d, d, g)
+    _lin(sd, "condition_embedder.time_proj", 6 * d, d, g)
+    _lin(sd, "condition_embedder.text_embedder.linear_1", d, cfg["text_dim"], g)
+    _lin(sd, "condition_embedder.text_embedder.linear_2", d, d, g)
+    _lin(sd, "proj_out", cfg["out_channels"] * math.prod(ps), d, g)
+    sd["scale_shift_table"] = (torch.randn(1, 2, d, generator=g) / d ** 0.5).to(dtype)
+    for i in range(cfg["num_layers"]):
+        sd.update(wan_block_state_dict(f"blocks.{i}", d, cfg["ffn_dim"], seed=seed * 100 + i, dtype=dtype))
+    return sd

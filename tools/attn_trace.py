@@ -39,3 +39,8 @@ for t in range(8, 20):
     print(line)
 per = (int(tr[0, 1, 40]) - int(tr[0, 1, 8])) / 32
 print("cycles per KV iteration (2 Q tiles x 128 keys):", per, " -> MMA-ideal 2048")
+life = [int(tr[3, 7, i]) for i in range(5)]
+last = max(int(tr[0, 5, t]) for t in range(64))
+print(f"CTA life cycle (cycles from kernel entry): set-up done {life[1]-life[0]}, first S ready {int(tr[0, 1, 0])-life[0]}, "
+      f"first P written {int(tr[0, 5, 0])-life[0]}, epilogue start {life[2]-life[0]}, epilogue end {life[3]-life[0]}, exit {life[4]-life[0]}"
+      f" | tiles in this launch: {s // 128}")
