@@ -43,7 +43,7 @@ SIGNATURES = {
                                  c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_int, c_void_p]),
     "fdm_layernorm_modulate_quant": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_int64, c_int64, c_int64, c_int64, c_int64, c_float,
-                                             c_int, c_int, c_int, c_void_p]),
+                                             c_int, c_int, c_int, c_int, c_void_p]),
     "fdm_ulysses_pack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),
     "fdm_rel_l1_distance": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "fdm_ulysses_unpack_heads": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, c_void_p]),

@@ -28,14 +28,15 @@ from .layers import FeedForward, QLinear, Quantized, load_linear, quantize
 
 
 class ModChunk:
-    """One AdaLN modulation vector [B, dim] whose two fp32 forms were prepared for all blocks at once by
-    `AdaLNTable` (one GEMM + two elementwise kernels per step instead of ~20 tiny launches per block):
-    `one_plus` = (1 + x) evaluated in the model dtype, widened to fp32; `f32` = x widened to fp32."""
+    """One AdaLN modulation vector [B, dim] whose forms were prepared for all blocks at once by `AdaLNTable` (one GEMM
+    + two elementwise kernels per step instead of ~20 tiny launches per block): `one_plus` = (1 + x) and `same` = x,
+    both in the model dtype (what the reference computes, normalization.py:196), `f32` = x widened to fp32 (the GEMM
+    epilogue takes its gate vectors in fp32)."""
 
-    __slots__ = ("one_plus", "f32")
+    __slots__ = ("one_plus", "same", "f32")
 
-    def __init__(self, one_plus: torch.Tensor, f32: torch.Tensor):
-        self.one_plus, self.f32 = one_plus, f32
+    def __init__(self, one_plus: torch.Tensor, same: torch.Tensor, f32: torch.Tensor):
+        self.one_plus, self.same, self.f32 = one_plus, same, f32
 
 
 def _f32(x) -> torch.Tensor:
@@ -43,11 +44,15 @@ def _f32(x) -> torch.Tensor:
 
 
 def _mod(scale, shift) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(1 + scale) evaluated in the tensor dtype as the reference does (normalization.py:196), then
-    widened to fp32 for the fused kernel (exact)."""
+    """((1 + scale), shift) for the fused LayerNorm-modulate kernel, evaluated in the tensor dtype as the reference
+    does (normalization.py:196). bf16 vectors are handed over as they are -- the kernel then runs the reference's
+    bf16 op chain as native packed bf16 instructions; other dtypes are widened to fp32 (exact)."""
     if isinstance(scale, ModChunk):
-        return scale.one_plus, shift.f32
-    return (1 + scale).float().contiguous(), shift.float().contiguous()
+        return scale.one_plus, shift.same
+    a, c = (1 + scale), shift
+    if a.dtype != torch.bfloat16:
+        a, c = a.float(), c.float()
+    return a.contiguous(), c.contiguous()
 
 
 class AdaLNTable:
@@ -74,16 +79,17 @@ class AdaLNTable:
             lin.bias = self.bias[o:o + n]
 
     def compute(self, cond: torch.Tensor):
-        """cond = silu(temb) [B, K] -> (one_plus, f32), both fp32 [B, sum N]."""
+        """cond = silu(temb) [B, K] -> (one_plus, same, f32): (1 + e) and e in the model dtype, e in fp32, [B, sum N]."""
         e = torch.addmm(self.bias, cond, self.weight_store.t())
-        return (1 + e).float(), e.float()
+        return (1 + e), e, e.float()
 
     def chunks(self, tables, index: int, n_chunks: int):
-        one_plus, f32 = tables
+        one_plus, same, f32 = tables
         o, n = self.offsets[index]
         d = n // n_chunks
+        # (batch 1: column slices of one row are contiguous as they are)
         mk = (lambda t, a: t[:, a:a + d]) if one_plus.shape[0] == 1 else (lambda t, a: t[:, a:a + d].contiguous())
-        return tuple(ModChunk(mk(one_plus, o + k * d), mk(f32, o + k * d)) for k in range(n_chunks))
+        return tuple(ModChunk(mk(one_plus, o + k * d), mk(same, o + k * d), mk(f32, o + k * d)) for k in range(n_chunks))
 
 
 class _JointDiTBlock:

@@ -8,6 +8,7 @@
 // per (token, head); arithmetic here follows the *torch backend* (fastdm/kernel/torch/*.py), which
 // is the parity oracle, not the reference CUDA formulas (SURVEY.md finding 0.6).
 #include <algorithm>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -988,6 +989,276 @@ __global__ void __launch_bounds__(512) ln_mod_quant_kernel(
   }
 }
 
+// Warp-per-row variant for the row widths the DiT blocks actually normalise (hidden sizes 1536 / 3072 / 5120,
+// i.e. <= 640 16-byte vectors): the row lives in one warp's registers (VPT <= 20 vectors per lane), both reductions
+// are five shuffles each -- no shared memory, no __syncthreads, every warp independent -- and the per-element work is
+// packed: f32x2 adds / multiplies for the statistics and the normalisation, and, when the modulation vectors arrive as
+// bf16 (MODBF: the reference evaluates (1 + scale) and shift in the tensor dtype, normalization.py:196), native
+// bf16x2 multiply / add / min / max on 16-byte loads of A and C. The CTA-per-row kernel above paid three block-wide
+// barriers per 10 KB row and 2.6x the instructions of the plain quant kernel (0.34 of HBM speed).
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t add2f(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2f(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t fma2f(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t bmin2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("min.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+
+// combine the partial results of the WPR warps that share a row (`slot` selects a shared-memory cell that is used
+// once, so no cell is ever rewritten while another warp of the group may still read it)
+template <int WPR>
+__device__ __forceinline__ void group_exchange(float& a, float& b, float2 (*cells)[8], int slot, bool take_min_max) {
+  if (WPR == 1) return;
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) cells[slot][w] = make_float2(a, b);
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + w / WPR), "n"(32 * WPR) : "memory");
+  const int w0 = w / WPR * WPR;
+  float2 acc = cells[slot][w0];
+#pragma unroll
+  for (int k = 1; k < WPR; ++k) {   // the same order in every warp: identical sums
+    const float2 o = cells[slot][w0 + k];
+    if (take_min_max) {
+      acc.x = fminf(acc.x, o.x);
+      acc.y = fmaxf(acc.y, o.y);
+    } else {
+      acc.x += o.x;
+      acc.y += o.y;
+    }
+  }
+  a = acc.x;
+  b = acc.y;
+}
+
+// 8 bf16 values (one 16-byte vector) -> 8 quantised bytes with the row's parameters; x / scale is the correctly
+// rounded quotient of div_by_scale(), evaluated two lanes at a time (f32x2) on the fast path
+template <int MODE, bool FAST>
+__device__ __forceinline__ void quantize_vec_bf16(const U128& v, const QParams& p, uint32_t& lo, uint32_t& hi) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  float q[8];
+  if (FAST) {
+    const uint64_t rcp2 = pk2(p.rcp, p.rcp), nscale2 = pk2(-p.scale, -p.scale), zp2 = pk2(p.zpf, p.zpf);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t f = pk2(bf16lo(w[k]), bf16hi(w[k]));
+      const uint64_t q0 = mul2f(f, rcp2);
+      uint64_t r = fma2f(fma2f(q0, nscale2, f), rcp2, q0);
+      if (MODE == 2) r = add2f(r, zp2);
+      upk2(r, q[2 * k], q[2 * k + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      q[2 * k] = __fdiv_rn(bf16lo(w[k]), p.scale);
+      q[2 * k + 1] = __fdiv_rn(bf16hi(w[k]), p.scale);
+      if (MODE == 2) {
+        q[2 * k] = __fadd_rn(q[2 * k], p.zpf);
+        q[2 * k + 1] = __fadd_rn(q[2 * k + 1], p.zpf);
+      }
+    }
+  }
+  if (MODE == 0) {
+    lo = cvt_e4m3x4(q[0], q[1], q[2], q[3]);
+    hi = cvt_e4m3x4(q[4], q[5], q[6], q[7]);
+  } else {
+    int c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(c[j]) : "f"(q[j]));
+    lo = (uint32_t)(c[0] & 0xff) | ((uint32_t)(c[1] & 0xff) << 8) | ((uint32_t)(c[2] & 0xff) << 16) | ((uint32_t)(c[3] & 0xff) << 24);
+    hi = (uint32_t)(c[4] & 0xff) | ((uint32_t)(c[5] & 0xff) << 8) | ((uint32_t)(c[6] & 0xff) << 16) | ((uint32_t)(c[7] & 0xff) << 24);
+  }
+}
+
+// EXACT: the row is exactly VPT * 32 * WPR vectors wide (1536 / 3072 / 5120 columns are): no per-vector bounds checks
+template <int MODE /*0 fp8, 2 int8 asym, 3 none*/, bool ROUND_STEPS, int VPT, bool MODBF, int WPR /*warps per row*/, bool EXACT>
+__global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 12 ? 2 : 1)))) ln_mod_quant_warp_kernel(
+    const __nv_bfloat16* __restrict__ in, const void* __restrict__ A, const void* __restrict__ C,
+    uint8_t* __restrict__ out, float* __restrict__ scale, int32_t* __restrict__ azp,
+    __nv_bfloat16* __restrict__ y_out, int64_t rows, int cols, int64_t in_row_stride, int64_t y_row_stride,
+    int64_t rows_per_batch, float eps) {
+  using T = __nv_bfloat16;
+  constexpr int LANES = 32 * WPR;   // lanes sharing a row
+  __shared__ float2 cells[3][8];
+  const int lane = threadIdx.x & (LANES - 1);
+  int64_t row = (int64_t)blockIdx.x * (256 / LANES) + (threadIdx.x / LANES);
+  // (a pair past the last row keeps running on the last row so that it still meets its barriers; it writes nothing new)
+  const bool live = row < rows;
+  if (!live) {
+    if (WPR == 1) return;
+    row = rows - 1;
+  }
+  const int nvec = cols >> 3;
+  const T* src = in + row * in_row_stride;
+  const int64_t bidx = row / rows_per_batch;
+  U128 raw[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = lane + i * LANES;
+    raw[i] = (EXACT || v < nvec) ? ldg128_stream(src + (int64_t)v * 8) : U128{0u, 0u, 0u, 0u};   // zeros add nothing to the sums
+  }
+  uint64_t sum2 = 0ull, sq2 = 0ull;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint64_t f = pk2(bf16lo(w[q]), bf16hi(w[q]));
+      sum2 = add2f(sum2, f);
+      sq2 = fma2f(f, f, sq2);
+    }
+  }
+  float s_lo, s_hi, q_lo, q_hi;
+  upk2(sum2, s_lo, s_hi);
+  upk2(sq2, q_lo, q_hi);
+  const float inv_n = 1.0f / (float)cols;
+  float rs = warp_sum(s_lo + s_hi), rq = warp_sum(q_lo + q_hi);
+  group_exchange<WPR>(rs, rq, cells, 0, false);
+  const float mean = rs * inv_n;
+  float var = fmaf(-mean, mean, rq * inv_n);
+  if (var < 1e-2f * mean * mean) {  // E[x^2] - mean^2 cancels: redo it centred (warp-uniform branch)
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      if (EXACT || lane + i * LANES < nvec) {
+        float f[8];
+        unpack8<T>(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[j] - mean;
+          sq = fmaf(d, d, sq);
+        }
+      }
+    }
+    float dummy = 0.f;
+    sq = warp_sum(sq);
+    group_exchange<WPR>(sq, dummy, cells, 1, false);
+    var = sq * inv_n;
+  }
+  const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+  const uint64_t nmean2 = pk2(-mean, -mean), rstd2 = pk2(rstd, rstd);
+  float mn = INFINITY, mx = -INFINITY;
+  uint32_t mn2 = 0x7f807f80u, mx2 = 0xff80ff80u;   // (+inf, +inf) / (-inf, -inf) as bf16 pairs
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int v = lane + i * LANES;
+    if (EXACT || v < nvec) {
+      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+      float n[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)   // (x - mean) * rstd: the two fp32 roundings of the element-wise kernel, two lanes at a time
+        upk2(mul2f(add2f(pk2(bf16lo(w[q]), bf16hi(w[q])), nmean2), rstd2), n[2 * q], n[2 * q + 1]);
+      if constexpr (MODBF) {
+        // y = T(T(T(n) * A) + C) on packed bf16 pairs (A, C bf16): three native instructions per pair
+        const U128 a = A ? ldg128(reinterpret_cast<const T*>(A) + bidx * cols + v * 8) : U128{0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
+        const U128 c = C ? ldg128(reinterpret_cast<const T*>(C) + bidx * cols + v * 8) : U128{0u, 0u, 0u, 0u};
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
+        uint32_t y[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t t2 = pack_bf16(n[2 * q], n[2 * q + 1]);
+          if (A) t2 = bmul2(t2, aw[q]);
+          if (C) t2 = badd2(t2, cw[q]);
+          y[q] = t2;
+          mn2 = bmin2(mn2, t2);
+          mx2 = bmax2(mx2, t2);
+        }
+        raw[i] = U128{y[0], y[1], y[2], y[3]};
+      } else {
+        const float* Ar = A ? reinterpret_cast<const float*>(A) + bidx * cols + v * 8 : nullptr;
+        const float* Cr = C ? reinterpret_cast<const float*>(C) + bidx * cols + v * 8 : nullptr;
+        float a[8], c[8];
+        if (Ar) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(Ar)), a1 = __ldg(reinterpret_cast<const float4*>(Ar + 4));
+          a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        }
+        if (Cr) {
+          const float4 c0 = __ldg(reinterpret_cast<const float4*>(Cr)), c1 = __ldg(reinterpret_cast<const float4*>(Cr + 4));
+          c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+        }
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = n[j];
+          if (ROUND_STEPS) {
+            t = round_to<T>(t);
+            if (Ar) t = round_to<T>(__fmul_rn(t, a[j]));
+            if (Cr) t = __fadd_rn(t, c[j]);
+          } else {
+            if (Ar) t = __fmul_rn(t, a[j]);
+            if (Cr) t = __fadd_rn(t, c[j]);
+          }
+          f[j] = t;
+        }
+        raw[i] = pack8<T>(f);
+        const uint32_t y[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          mn2 = bmin2(mn2, y[q]);
+          mx2 = bmax2(mx2, y[q]);
+        }
+      }
+      if (y_out && live) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
+    }
+  }
+  if (MODE == 3) return;   // (no barrier follows)
+  mn = warp_min(fminf(bf16lo(mn2), bf16hi(mn2)));
+  mx = warp_max(fmaxf(bf16lo(mx2), bf16hi(mx2)));
+  group_exchange<WPR>(mn, mx, cells, 2, true);
+  if (!live) return;
+  const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(mn, mx, fp8_amax_floor<T>());
+  if (lane == 0) {
+    scale[row] = p.scale;
+    if (MODE == 2) azp[row] = p.zp;
+  }
+  uint8_t* dst = out + row * (int64_t)cols;
+  if (p.fast) {   // row-uniform: one branch per row
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int v = lane + i * LANES;
+      if (EXACT || v < nvec) {
+        uint32_t lo, hi;
+        quantize_vec_bf16<MODE == 3 ? 0 : MODE, true>(raw[i], p, lo, hi);
+        stg64(dst + (int64_t)v * 8, lo, hi);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int v = lane + i * LANES;
+      if (EXACT || v < nvec) {
+        uint32_t lo, hi;
+        quantize_vec_bf16<MODE == 3 ? 0 : MODE, false>(raw[i], p, lo, hi);
+        stg64(dst + (int64_t)v * 8, lo, hi);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Ulysses layout helpers: [S, H, hd] <-> [P, S, H/P, hd], 16-byte vectors
 // ------------------------------------------------------------------------------------------------
@@ -1253,12 +1524,48 @@ static void launch_lnq(const void* in, const float* A, const float* C, void* out
 #undef LNQ
 }
 
+// row-in-registers kernel: rows of up to 640 vectors (5120 columns), shared by 1, 2 or 4 warps (FDM_LNQ_WPR
+// overrides the choice for experiments)
+template <int MODE, bool RS, bool MODBF>
+static void launch_lnq_warp(const void* in, const void* A, const void* C, void* out, float* scale, int32_t* azp, void* y,
+                            int64_t rows, int cols, int64_t is, int64_t ys, int64_t rpb, float eps, cudaStream_t st) {
+  const int nvec = cols / 8;
+  static const int forced = [] { const char* e = getenv("FDM_LNQ_WPR"); return e ? atoi(e) : 0; }();
+  // measured on [80640, 5120]: 2 warps per row 265 / 370 / 344 us (bf16 vectors / fp32 vectors / fp32 chain), 4 warps
+  // 261 / 419 / 354 us, 1 warp (20 vectors per lane, 200 registers) 517 / 688 / 558 us
+  int wpr = forced ? forced : (nvec <= 96 ? 1 : 2);
+#define LNQW(V, W)                                                                                                      \
+  do {                                                                                                                  \
+    if (nvec == V * 32 * W)                                                                                             \
+      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true><<<(unsigned)((rows + 8 / W - 1) / (8 / W)), 256, 0, st>>>(  \
+          (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps);  \
+    else                                                                                                                \
+      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, false><<<(unsigned)((rows + 8 / W - 1) / (8 / W)), 256, 0, st>>>( \
+          (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps);  \
+  } while (0)
+  const int vpt = (nvec + 32 * wpr - 1) / (32 * wpr);
+  if (wpr == 1) {
+    if (vpt <= 3) LNQW(3, 1);
+    else if (vpt <= 6) LNQW(6, 1);
+    else if (vpt <= 12) LNQW(12, 1);
+    else LNQW(20, 1);
+  } else if (wpr == 2) {
+    if (vpt <= 3) LNQW(3, 2);
+    else if (vpt <= 6) LNQW(6, 2);
+    else LNQW(10, 2);
+  } else {
+    if (vpt <= 3) LNQW(3, 4);
+    else LNQW(5, 4);
+  }
+#undef LNQW
+}
+
 extern "C" {
 
-int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* add, void* out,
+int fdm_layernorm_modulate_quant(const void* in, const void* mul, const void* add, void* out,
                                  float* scale, int32_t* azp, void* y_out, int64_t rows, int64_t cols,
                                  int64_t in_row_stride, int64_t y_row_stride, int64_t rows_per_batch,
-                                 float eps, int round_steps, int in_dtype, int out_dtype,
+                                 float eps, int round_steps, int in_dtype, int out_dtype, int mod_dtype,
                                  void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
@@ -1269,8 +1576,9 @@ int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* 
   FDM_REQUIRE(cols % 8 == 0 && cols <= 512 * 8 * 8 && in_row_stride % 8 == 0 &&
                   (uintptr_t)in % 16 == 0,
               "layernorm_modulate_quant: cols must be a multiple of 8 (<= 32768), 16-byte aligned rows");
+  FDM_REQUIRE(mod_dtype == FDM_F32 || mod_dtype == FDM_BF16, "layernorm_modulate_quant: mul/add must be fp32 or bf16");
   FDM_REQUIRE((mul == nullptr || (uintptr_t)mul % 16 == 0) && (add == nullptr || (uintptr_t)add % 16 == 0),
-              "layernorm_modulate_quant: mul/add must be 16-byte aligned fp32");
+              "layernorm_modulate_quant: mul/add must be 16-byte aligned");
   FDM_REQUIRE(y_out == nullptr || (y_row_stride % 8 == 0 && (uintptr_t)y_out % 16 == 0),
               "layernorm_modulate_quant: y_out alignment");
   FDM_REQUIRE(rows < (1LL << 31) && (rows + rows_per_batch - 1) / rows_per_batch < 65536,
@@ -1285,13 +1593,43 @@ int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   using B = __nv_bfloat16;
   const int c = (int)cols;
+  const bool modbf = mod_dtype == FDM_BF16 && (mul != nullptr || add != nullptr);
+  // bf16 modulation vectors are the reference's bf16 chain T(T(T(LN(x)) * A) + C) by construction
+  FDM_REQUIRE(!modbf || round_steps, "layernorm_modulate_quant: bf16 mul/add imply round_steps (the bf16 op chain)");
+  static const bool warp_rows = [] { const char* e = getenv("FDM_LNQ_WARP"); return e == nullptr || atoi(e) != 0; }();
+  if (c <= 640 * 8 && warp_rows) {
+#define LNQW_CALL(MODE)                                                                                              \
+  do {                                                                                                               \
+    if (modbf)                                                                                                       \
+      launch_lnq_warp<MODE, true, true>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride, y_row_stride,  \
+                                        rows_per_batch, eps, st);                                                    \
+    else if (round_steps)                                                                                            \
+      launch_lnq_warp<MODE, true, false>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride, y_row_stride, \
+                                         rows_per_batch, eps, st);                                                   \
+    else                                                                                                             \
+      launch_lnq_warp<MODE, false, false>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride, y_row_stride, \
+                                          rows_per_batch, eps, st);                                                  \
+  } while (0)
+    if (q8) LNQW_CALL(0);
+    else if (s8) LNQW_CALL(2);
+    else LNQW_CALL(3);
+#undef LNQW_CALL
+    FDM_LAUNCH_CHECK("layernorm_modulate_quant kernel launch");
+    return FDM_OK;
+  }
+  if (modbf) {
+    set_error("layernorm_modulate_quant: bf16 mul/add are built for rows of up to 5120 columns");
+    return FDM_ERR_UNSUPPORTED;
+  }
+  const float* mulf = (const float*)mul;
+  const float* addf = (const float*)add;
 #define LNQ_CALL(MODE)                                                                               \
   do {                                                                                               \
     if (round_steps)                                                                                 \
-      launch_lnq<B, MODE, true>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride,        \
+      launch_lnq<B, MODE, true>(in, mulf, addf, out, scale, azp, y_out, rows, c, in_row_stride,      \
                                 y_row_stride, rows_per_batch, eps, st);                              \
     else                                                                                             \
-      launch_lnq<B, MODE, false>(in, mul, add, out, scale, azp, y_out, rows, c, in_row_stride,       \
+      launch_lnq<B, MODE, false>(in, mulf, addf, out, scale, azp, y_out, rows, c, in_row_stride,     \
                                  y_row_stride, rows_per_batch, eps, st);                             \
   } while (0)
   if (q8) LNQ_CALL(0);

@@ -386,10 +386,19 @@ def _ln_mod_quant(x: torch.Tensor, mul: Optional[torch.Tensor], add: Optional[to
     if x.ndim != 2 or x.stride(1) != 1 or x.dtype != torch.bfloat16:
         raise RuntimeError(f"fastdm_b200.{what}: x must be bf16 [rows, cols] with unit column stride")
     rows, cols = x.shape
+    mod_dt = None
     for t in (mul, add):
-        if t is not None and (t.dtype != torch.float32 or t.ndim != 2 or t.shape[1] != cols or not t.is_contiguous()
-                              or t.shape[0] * rows_per_batch < rows):
-            raise RuntimeError(f"fastdm_b200.{what}: mul/add must be contiguous float32 [batches, cols] covering all rows")
+        if t is None:
+            continue
+        if t.dtype not in (torch.float32, torch.bfloat16) or t.ndim != 2 or t.shape[1] != cols or not t.is_contiguous() \
+                or t.shape[0] * rows_per_batch < rows or (mod_dt is not None and t.dtype != mod_dt):
+            raise RuntimeError(f"fastdm_b200.{what}: mul/add must be contiguous [batches, cols] covering all rows, both "
+                               f"float32 or both bfloat16")
+        mod_dt = t.dtype
+    if mod_dt == torch.bfloat16 and (not round_steps or cols > 5120):
+        # bf16 vectors are the bf16 op chain (round_steps) on the warp-per-row kernel; anything else takes them as fp32
+        mul, add = (None if t is None else t.float() for t in (mul, add))
+        mod_dt = torch.float32
     dev = x.device
     qdt = {FDM_E4M3: torch.float8_e4m3fn, FDM_S8: torch.int8}.get(out_code)
     q = torch.empty((rows, cols) if qdt is not None else (0, cols), device=dev, dtype=qdt or torch.int8)
@@ -402,7 +411,7 @@ def _ln_mod_quant(x: torch.Tensor, mul: Optional[torch.Tensor], add: Optional[to
             scale.data_ptr() if qdt is not None else None, azp.data_ptr() if out_code == FDM_S8 else None,
             y.data_ptr() if want_y else None, rows, cols, x.stride(0) if rows > 1 else cols, cols,
             max(rows_per_batch, 1), float(eps), 1 if round_steps else 0, FDM_BF16,
-            out_code if qdt is not None else FDM_BF16, _stream(x))
+            out_code if qdt is not None else FDM_BF16, FDM_BF16 if mod_dt == torch.bfloat16 else FDM_F32, _stream(x))
     _lib.check(rc, what)
     return q, scale, azp, y
 

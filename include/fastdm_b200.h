@@ -111,15 +111,17 @@ int fdm_qk_norm_rope(void* buf, const void* wq, const void* wk, const void* cos_
  *       fastdm/layer/normalization.py:191-199,228-234; fastdm/model/flux.py:156-158,170-171
  *   round_steps = 0 (Wan, fp32 chain):              y = T(LN(x) * mul + add)
  *       fastdm/model/wan.py:95,108 (mul = 1+scale, add = shift) and :101 (mul = weight, add = bias)
- *   mul / add  fp32 [batches, cols] or NULL; row r uses batch r / rows_per_batch
+ *   mul / add  [batches, cols] or NULL, both of mod_dtype: FDM_F32, or FDM_BF16 (round_steps = 1 only: the
+ *              reference evaluates (1 + scale) and shift in the tensor dtype, so bf16 loses nothing and the
+ *              chain runs as native packed bf16 instructions); row r uses batch r / rows_per_batch
  *   out_dtype  FDM_E4M3 -> out + scale[rows]; FDM_S8 -> out + scale + azp (asymmetric);
  *              anything else -> no quantised output (y_out required)
  *   y_out      optional bf16 copy of y (row stride y_row_stride), NULL to skip
  * The quantised codes equal fdm_quant_*(y) bit for bit. */
-int fdm_layernorm_modulate_quant(const void* in, const float* mul, const float* add, void* out,
+int fdm_layernorm_modulate_quant(const void* in, const void* mul, const void* add, void* out,
                                  float* scale, int32_t* azp, void* y_out, int64_t rows, int64_t cols,
                                  int64_t in_row_stride, int64_t y_row_stride, int64_t rows_per_batch,
-                                 float eps, int round_steps, int in_dtype, int out_dtype,
+                                 float eps, int round_steps, int in_dtype, int out_dtype, int mod_dtype,
                                  void* stream);
 
 /* out[r, :d] = x[r, :d] * gelu_erf(x[r, d:2d])   (second half gated).

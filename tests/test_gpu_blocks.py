@@ -176,6 +176,66 @@ def test_layernorm_modulate_quant_equals_unfused(lib):
     assert float((y != want).float().mean()) < 5e-3
 
 
+@pytest.mark.parametrize("d", [1536, 3072, 5120, 6144, 1000])
+def test_layernorm_modulate_quant_all_paths(lib, d):
+    """Every kernel / argument form of the fused LayerNorm-modulate-quant: the warp-per-row kernel (d <= 5120) with bf16
+    modulation vectors (packed bf16 chain), with fp32 vectors (element-wise chain) and the fp32 Wan chain; the
+    CTA-per-row kernel for wider rows (d = 6144); a width that is not a multiple of 256 (d = 1000); missing mul / add.
+    bf16 and fp32 forms of the same bf16-valued vectors must agree bit for bit, codes must equal quantising y."""
+    import torch.nn.functional as F
+
+    from fastdm_b200 import ops
+
+    g = torch.Generator().manual_seed(d)
+    Bn, S = 2, 173
+    x = (torch.randn(Bn * S, d, generator=g) * 2 + 0.3).to(BF).to(DEV)
+    x[5] = 7.0                      # constant row: variance 0, LN = 0, y = shift
+    x[6, :] = 1000.0
+    x[6, 3] = 1001.0                # the E[x^2] - mean^2 cancellation branch
+    scale = (torch.randn(Bn, d, generator=g) * 0.2).to(BF).to(DEV)
+    shift = (torch.randn(Bn, d, generator=g) * 0.2).to(BF).to(DEV)
+    a16, c16 = (1 + scale), shift
+    want = (F.layer_norm(x.view(Bn, S, d), (d,), None, None, 1e-6) * a16[:, None] + c16[:, None]).view(Bn * S, d)
+    ok = torch.ones(Bn * S, dtype=torch.bool, device=DEV)
+    ok[6] = False                   # torch's own bf16 LayerNorm loses this row to cancellation; checked on its own below
+    for quant in (torch.float8_e4m3fn, torch.int8):
+        qb, sb, zb, yb = ops.layernorm_modulate_quant(x, a16, c16, S, quant, 1e-6, round_steps=True, want_y=True)
+        qf, sf, zf, yf = ops.layernorm_modulate_quant(x, a16.float(), c16.float(), S, quant, 1e-6, round_steps=True, want_y=True)
+        assert torch.equal(yb, yf) and torch.equal(qb.view(torch.uint8), qf.view(torch.uint8)) and torch.equal(sb, sf)
+        assert float((yb.float() - want.float())[ok].abs().max()) <= 0.07
+        assert float((yb != want)[ok].float().mean()) < 5e-3
+        if quant == torch.int8:
+            rq, rs, rzp = ops.quantize_to_int8(yb, False)
+            # (constant rows have max == min: scale 0, NaN codes in the reference too -- compare the others)
+            live = (yb.float().amax(1) > yb.float().amin(1))
+            assert torch.equal(qb[live], rq[live]) and torch.equal(sb[live], rs[live]) and torch.equal(zb[live], rzp[live])
+        else:
+            rq, rs = ops.quantize_to_fp8(yb)
+            assert torch.equal(qb.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(sb, rs)
+    # the cancellation row: mean 1000 + 1/d, one element 1 above the rest
+    ln6 = F.layer_norm(x[6:7].float(), (d,), None, None, 1e-6)
+    y6 = (ln6.to(BF) * a16[0:1]).to(BF) + c16[0:1]
+    assert float((yb[6:7].float() - y6.float()).abs().max()) <= 0.07 * max(1.0, float(ln6.abs().max()) / 4)
+    # only mul, only add, neither
+    for (a, c) in ((a16, None), (None, c16), (None, None)):
+        want1 = F.layer_norm(x.view(Bn, S, d), (d,), None, None, 1e-6)
+        if a is not None:
+            want1 = want1 * a[:, None]
+        if c is not None:
+            want1 = want1 + c[:, None]
+        _, _, _, y1 = ops.layernorm_modulate_quant(x, a, c, S, None, 1e-6, round_steps=True)
+        assert float((y1 != want1.view(Bn * S, d))[ok].float().mean()) < 5e-3
+    # Wan chain (fp32 vectors, one rounding): wan.py:95
+    sc32 = scale.float() + 1e-3 * torch.randn(Bn, d, generator=g).to(DEV)     # not bf16-valued
+    want = (F.layer_norm(x.view(Bn, S, d).float(), (d,), None, None, 1e-6) * (1 + sc32[:, None]) + shift.float()[:, None]).to(BF)
+    q, s_, _, y = ops.layernorm_modulate_quant(x, 1 + sc32, shift.float(), S, torch.float8_e4m3fn, 1e-6, round_steps=False, want_y=True)
+    want = want.view(Bn * S, d)
+    assert float((y.float() - want.float())[ok].abs().max()) <= 0.04
+    assert float((y != want)[ok].float().mean()) < 5e-3
+    rq, rs = ops.quantize_to_fp8(y)
+    assert torch.equal(q.view(torch.uint8), rq.view(torch.uint8)) and torch.equal(s_, rs)
+
+
 def test_gemm_gate_residual_epilogue_equals_unfused(lib):
     from fastdm_b200 import ops
 

@@ -244,17 +244,26 @@ def block_kernels_perf():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / iters
 
-    for (M, K) in ((8704, 3072), (8704, 15360), (80640, 5120)):
+    for (M, K) in ((8704, 3072), (8704, 1536), (80640, 5120)):
         nbuf = max(2, int(400e6 // (M * K * 2)) + 1)
         a = (torch.rand(1, K, device=DEV) + 0.5).to(BF).float()   # bf16-valued, as the AdaLN chain produces them
         c = torch.rand(1, K, device=DEV).to(BF).float()
         ms = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF),
                       lambda x: ops.layernorm_modulate_quant(x, a, c, M, torch.float8_e4m3fn), nbuf)
         gb = (3 * M * K + 4 * M) / ms / 1e6
+        a16, c16 = a.to(BF), c.to(BF)
+        msb = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF),
+                       lambda x: ops.layernorm_modulate_quant(x, a16, c16, M, torch.float8_e4m3fn), nbuf)
+        gbb = (3 * M * K + 4 * M) / msb / 1e6
+        a32 = a + 1e-4   # not bf16-valued: the Wan fp32 chain
+        msw = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF),
+                       lambda x: ops.layernorm_modulate_quant(x, a32, c, M, torch.float8_e4m3fn, round_steps=False), nbuf)
+        gbw = (3 * M * K + 4 * M) / msw / 1e6
         ms2 = rot_time(lambda: torch.randn(M, K, device=DEV, dtype=BF), lambda x: ops.quantize_to_fp8(x), nbuf)
         gb2 = (3 * M * K + 4 * M) / ms2 / 1e6
-        print(f"[{M},{K}] ln_mod_quant {ms*1e3:.1f} us {gb:.0f} GB/s | quant_fp8 {ms2*1e3:.1f} us {gb2:.0f} GB/s")
-        res[f"lnq_{M}x{K}"] = dict(lnq_us=ms * 1e3, lnq_gbs=gb, quant_us=ms2 * 1e3, quant_gbs=gb2)
+        print(f"[{M},{K}] ln_mod_quant fp32 mods {ms*1e3:.1f} us {gb:.0f} GB/s | bf16 mods {msb*1e3:.1f} us {gbb:.0f} GB/s | "
+              f"fp32 chain (Wan) {msw*1e3:.1f} us {gbw:.0f} GB/s | quant_fp8 {ms2*1e3:.1f} us {gb2:.0f} GB/s")
+        res[f"lnq_{M}x{K}"] = dict(lnq_us=ms * 1e3, lnq_gbs=gb, lnq_bf16mod_gbs=gbb, lnq_wan_gbs=gbw, quant_us=ms2 * 1e3, quant_gbs=gb2)
     for (S, H, across) in ((8704, 24, False), (80640, 40, True)):
         d = H * 128
         nbuf = max(2, int(400e6 // (S * 3 * d * 2)) + 1)
