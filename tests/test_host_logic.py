@@ -32,16 +32,21 @@ def test_adaln_table_equals_separate_linears():
         assert len(chunks) == n_chunks and all(isinstance(c, ModChunk) for c in chunks)
         ref = w.chunk(n_chunks, dim=1)
         for c, r in zip(chunks, ref):
-            assert c.f32.is_contiguous() and c.one_plus.is_contiguous()
+            assert c.f32.is_contiguous() and c.one_plus.is_contiguous() and c.same.is_contiguous()
+            assert c.one_plus.dtype == torch.bfloat16 and c.same.dtype == torch.bfloat16 and c.f32.dtype == torch.float32
             # same dot products; the stacked GEMM may round a few last bits differently than the small one
             assert torch.allclose(c.f32, r.float(), rtol=2e-2, atol=2e-2)
             a, cc = _mod(c, c)
-            assert torch.equal(a, c.one_plus) and torch.equal(cc, c.f32) and torch.equal(_f32(c), c.f32)
-            assert torch.equal(c.one_plus, (1 + c.f32.to(torch.bfloat16)).float())   # (1 + x) evaluated in bf16
+            # the fused LayerNorm-modulate kernel takes (1 + scale) and shift in the model dtype; gates stay fp32
+            assert torch.equal(a, c.one_plus) and torch.equal(cc, c.same) and torch.equal(_f32(c), c.f32)
+            assert torch.equal(c.same.float(), c.f32)
+            assert torch.equal(c.one_plus, 1 + c.same)                               # (1 + x) evaluated in bf16
 
 
 def test_mod_helpers_on_plain_tensors():
     x = torch.randn(2, 8).to(torch.bfloat16)
     a, c = _mod(x, x)
-    assert a.dtype == torch.float32 and torch.equal(a, (1 + x).float()) and torch.equal(c, x.float())
+    assert a.dtype == torch.bfloat16 and torch.equal(a, 1 + x) and torch.equal(c, x)     # bf16 stays bf16
     assert torch.equal(_f32(x), x.float())
+    a, c = _mod(x.half(), x.half())                                                       # other dtypes widen to fp32
+    assert a.dtype == torch.float32 and torch.equal(a, (1 + x.half()).float()) and torch.equal(c, x.half().float())
