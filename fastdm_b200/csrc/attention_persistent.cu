@@ -28,13 +28,27 @@
 // Semantics: fastdm/kernel/torch/attention.py:7-43 (F.scaled_dot_product_attention, non-causal),
 // checked against the fp32 reference of tests/test_attention.py:23-63 at atol 1.8e-2 (:94).
 // Replaces the library routes of fastdm/kernel/cuda/attention.py:149-261.
+// Persistent variant of the flash-attention forward kernel (csrc/attention.cu) for calls whose KV sequence is short:
+// one CTA (pair) per SM (pair) loops over its (query block, head, batch) work items with the barrier phases running
+// on, so that an item's Q / K loads and first QK^T overlap the previous item's last tiles and epilogue -- the ~10-20 us
+// of per-CTA set-up, first loads and epilogue are most of a CTA's life when it only has 4 KV tiles (Wan cross-attention
+// onto 512 text tokens: 0.79 -> 1.07 PFLOP/s) and irrelevant when it has 630.
+//
+// A separate translation unit, and a near-copy of the one-item kernel, on purpose: with the item loop around it ptxas
+// schedules the softmax and MMA-issue loops measurably worse (the same source compiled with the loop folded away still
+// came out 4-12 % slower than the original on 68- to 630-tile calls; A/B runs of tools/attn_ab.py, profiles/r02_*), so
+// the long-sequence kernel keeps its file -- and its instruction schedule -- untouched.
+//
+// Everything else (roles, TMEM / shared-memory layout, softmax) is as described in attention.cu.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 
 #include "sm100.cuh"
 
 namespace fdm {
+namespace pst {
 using namespace sm100;
 
 constexpr int kAttnThreads = 384;  // 2 softmax warpgroups + 1 warpgroup hosting the TMA and MMA warps
@@ -54,7 +68,7 @@ struct AttnSmem {
   static constexpr int kPOff = 2 * kTileBytes;
   static constexpr int kKvOff = kPOff + 2 * kPBytes;
   static constexpr int kBarOff = kKvOff + kStages * kKvBytes;
-  static constexpr int kNumBars = 1 + 2 * kStages + 8;
+  static constexpr int kNumBars = 1 + 2 * kStages + 8 + 3;  // q_full | kv ring | 8 per-Q-tile | q_empty, o_free x 2
   static constexpr int kFlagsOff = kBarOff + kNumBars * 8 + 16;
   static constexpr int kTotal = kFlagsOff + kMaxKvTiles / 8 + 1024;  // one flag bit per KV tile; 1 KB alignment slack
   static_assert(kTotal <= 232448, "attention: shared-memory layout exceeds 227 KB");
@@ -67,9 +81,10 @@ struct AttnParams {
   const int8_t* mask;
   int B, H, Sq, Sk;
   int n_kv_tiles;
+  int nqb;            // work items along the query axis: blocks of 2 * CG Q tiles
+  uint32_t n_items;   // nqb * H * B; the grid's CTAs (pairs) loop over them (persistent for dense calls)
   int mask_bq, mask_bk, nbq, nbk;
   float scale_log2;
-  int reserved;      // (kept: the layout of this struct is part of the measured build, see attention_persistent.cu)
   long long* trace;  // debug: per-event clock64 stamps of CTA (0,0,0), or nullptr
 };
 
@@ -176,6 +191,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr bool F16 = DT == kDtF16;
   constexpr int EMU = EMUX & 63;           // exponentials per 32 that run on the FMA pipe
   constexpr bool LS = (EMUX & 64) != 0;    // late store: the whole P tile is packed in registers before it is written
+  // persistent: the CTA (pair) loops over work items. Compiled out otherwise (one item per CTA): the item loops below
+  // then run exactly once and the running counters `g` / `it` fold to zero -- the tile loop of the long-sequence
+  // kernel keeps the register allocation and instruction schedule it has without them (measured 7-16 % apart)
+  constexpr bool PERSIST = (EMUX & 128) != 0 && !MASKED;
   static_assert(CG == 1 || (PS && HD == 128 && ES == 2), "the CTA-pair variant is built for hd 128, 16-bit operands, P in smem");
   using S = AttnSmem<HD, ES, PS, CG>;
   // hd 64 leaves half of each O block of TMEM unused: P goes there (PT) instead of over S, so -- exactly as with
@@ -196,6 +215,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_ready = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 2 + x); };
   auto o_done = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 4 + x); };
   auto s_free = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 6 + x); };
+  const uint32_t q_empty = bar_base + 8u * (1 + 2 * S::kStages + 8);           // the item's last QK has read Q
+  auto o_free = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 9 + x); };  // the epilogue has read O_X
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S::kBarOff + S::kNumBars * 8);
   uint8_t* flags = smem + S::kFlagsOff;
 
@@ -211,12 +232,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   };
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * kQTile;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  // Work items: (query block of 2 * CG Q tiles, head, batch), query block fastest so that concurrently running CTAs
+  // stream the same K / V. A dense call is launched persistent -- one CTA (pair) per SM (pair), looping over its items
+  // with the barrier phases simply running on -- so that an item's Q / K loads and first QK^T overlap the previous
+  // item's last tiles and epilogue; a masked call gets one CTA (pair) per item (its active-tile list is built once).
+  // (one item per CTA: the grid is (query blocks, heads, batch) and the item is read off blockIdx)
+  const uint32_t cluster_id = PERSIST ? blockIdx.x / CG : blockIdx.x / CG + (blockIdx.y + blockIdx.z * gridDim.y) * (uint32_t)p.nqb;
+  const uint32_t n_clusters = gridDim.x / CG;
+  auto item_q0 = [&](uint32_t item) {
+    return PERSIST ? (int)(((item % (uint32_t)p.nqb) * CG + rank) * 2 * kQTile) : (int)(blockIdx.x * 2 * kQTile);
+  };
+  auto item_h = [&](uint32_t item) { return PERSIST ? (int)((item / (uint32_t)p.nqb) % (uint32_t)p.H) : (int)blockIdx.y; };
+  auto item_b = [&](uint32_t item) { return PERSIST ? (int)(item / ((uint32_t)p.nqb * (uint32_t)p.H)) : (int)blockIdx.z; };
   constexpr bool has_mask = MASKED;  // a block mask was passed (p.mask != nullptr)
   auto trace_ev = [&](const AttnParams& pp, bool on, int role, int ev, uint32_t tile) { trace_ev_t<TRACE>(pp, on, role, ev, tile); };
-  const int8_t* mask_bh = has_mask ? p.mask + ((int64_t)b * p.H + h) * p.nbq * p.nbk : nullptr;
+  // (masked calls: exactly one item per CTA / pair)
+  const int8_t* mask_bh = has_mask ? p.mask + ((int64_t)blockIdx.z * p.H + blockIdx.y) * p.nbq * p.nbk : nullptr;
 
   // TRACE: CTA life-cycle stamps in trace[(3 * 8 + 7) * 64 + i]: 0 kernel entry, 1 set-up done, 2 epilogue start, 3 epilogue
   // end, 4 kernel exit
@@ -237,7 +268,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // single CTA: one arrival per softmax thread; CTA pair: one elected arrival per softmax warp of both CTAs
       mbar_init(p_ready(x), CG == 2 ? 8 : 128);
       mbar_init(s_free(x), CG == 2 ? 8 : 128);
+      mbar_init(o_free(x), CG == 2 ? 8 : 128);
     }
+    mbar_init(q_empty, 1);
     fence_mbar_init();
   }
   if (warp == 9) tmem_alloc<CG>(smem_u32(tmem_ptr_smem), 512);
@@ -291,8 +324,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * CG * S::kTileBytes);
       const uint32_t q_full_lead = lead(q_full);
+      uint32_t u = 0;   // ring items issued so far (runs on across work items)
+      uint32_t it = 0;  // work items started by this CTA
+      uint32_t item = cluster_id;
+      do {
+      const int q0 = item_q0(item), h = item_h(item), b = item_b(item);
+      // the Q tiles are read by every QK^T of the previous item: wait for its last one
+      if (it > 0) mbar_wait(q_empty, (it - 1) & 1u);
+      if (rank == 0) mbar_arrive_expect_tx(q_full, 2 * CG * S::kTileBytes);
 #pragma unroll
       for (int x = 0; x < 2; ++x)
 #pragma unroll
@@ -301,7 +341,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (CG == 2) tma_load_4d_cg2(dst, &tmap_q, q_full_lead, hf * kBoxElems, h, q0 + x * kQTile, b);
           else tma_load_4d(dst, &tmap_q, q_full, hf * kBoxElems, h, q0 + x * kQTile, b);
         }
-      uint32_t u = 0;
       auto load_tile = [&](const CUtensorMap* tm, int j) {
         const int stage = u % S::kStages;
         const uint32_t parity = ((u / S::kStages) & 1u) ^ 1u;
@@ -344,6 +383,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           load_tile(&tmap_v, j);
         }
       }
+      } while (PERSIST && (++it, (item += n_clusters) < p.n_items));  // work items
     }
     __syncwarp();
   } else if (warp == 9) {
@@ -400,46 +440,64 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (ks == (kKvTile / kKeysPerPV) * 7 / 8 - 1) probe();
         }
       };
-      auto stage_addr = [&](uint32_t u) { return base + S::kKvOff + (u % S::kStages) * S::kKvBytes; };
-      auto wait_full = [&](uint32_t u) {
-        mbar_wait(kv_full(u % S::kStages), (u / S::kStages) & 1u);
-        tc_fence_after();
+      auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
+      auto ring_next = [&](uint32_t& st, uint32_t& par) {
+        if (++st == (uint32_t)S::kStages) {
+          st = 0;
+          par ^= 1u;
+        }
       };
       const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
 
+      // State that runs on across work items: the K/V ring cursor (stage, parity of its full barrier), the number of
+      // KV tiles issued so far `g` (the phases of s_full / s_free / p_ready / o_done count tiles, whichever item they
+      // belong to) and the number of items `it` (phases of q_full / q_empty / o_free).
+      uint32_t st = 0, par = 0, g = 0, it = 0;
+      uint32_t item = cluster_id;
+      do {
       int j = next_active(0);
-      if (j < p.n_kv_tiles) {
-        mbar_wait(q_full, 0);
-        tc_fence_after();
-        wait_full(0);
+      if (j >= p.n_kv_tiles) continue;   // (masked call whose query block attends to nothing: its one and only item)
+      mbar_wait(q_full, it & 1u);
+      mbar_wait(kv_full(st), par);
+      if (PERSIST && g > 0) {
+        // the previous item's last S tiles have to be in the softmax warps' registers (DEC), or consumed as P by its
+        // last PV, which the tensor pipe runs before anything issued from here on (!DEC)
         if (DEC) {
+          mbar_wait(s_free(0), (g - 1) & 1u);
+          mbar_wait(s_free(1), (g - 1) & 1u);
+        }
+      }
+      tc_fence_after();
+      // PV_X(first tile) overwrites O_X: the previous item's epilogue must have read it. (A macro, not a lambda: a
+      // closure capturing the item counters by reference parks them in local memory, and every extra dependent
+      // instruction of this thread's loop -- let alone a local load -- delays the next group of MMAs.)
+#define FDM_WAIT_O_FREE(x, t)                   \
+  if (PERSIST && (t) == 0 && it > 0) {          \
+    mbar_wait(o_free(x), (it - 1) & 1u);        \
+    tc_fence_after();                           \
+  }
+      issue_qk(0, stage_smem(st), no_probe);
+      commit(s_full(0));
+      issue_qk(1, stage_smem(st), no_probe);
+      commit(s_full(1));
+      commit(kv_empty(st));
+      ring_next(st, par);
+      int jn = next_active(j + 1);
+      if (PERSIST && jn >= p.n_kv_tiles) commit(q_empty);   // single-tile item: Q is done with
+      if (DEC) {
           // P travels through shared memory (or spare TMEM columns), so S_X is free again as soon as the softmax warps hold it in
           // registers: QK_X(t+1) is issued ahead of PV_X(t) and the only per-tile dependency chain left is
           // the softmax itself. Per active tile t the groups go QK_A(t+1), PV_A(t), QK_B(t+1), PV_B(t); ring
           // items (order of first use): K(0) | K(t+1), V(t) | ... While a group is being issued the barriers
           // of the NEXT group are probed without blocking; only if they have not completed by the end of the
           // group does the thread fall back to a blocking wait (a real dependency stall).
-          auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
-          auto ring_next = [&](uint32_t& st, uint32_t& par) {
-            if (++st == (uint32_t)S::kStages) {
-              st = 0;
-              par ^= 1u;
-            }
-          };
-          issue_qk(0, stage_smem(0), no_probe);
-          commit(s_full(0));
-          issue_qk(1, stage_smem(0), no_probe);
-          commit(s_full(1));
-          commit(kv_empty(0));
-          uint32_t st = 1u % S::kStages, par = 0u;  // ring cursor: item 1 = K(1) (or V(0) if there is no tile 1)
           uint32_t t = 0;
           bool ok = false;  // "the barriers of the group about to be issued were seen complete by a probe"
-          int jn = next_active(j + 1);
           while (true) {
             const bool has_next = jn < p.n_kv_tiles;
             const int jn2 = has_next ? next_active(jn + 1) : jn;
             const bool has_next2 = has_next && jn2 < p.n_kv_tiles;
-            const uint32_t ph = t & 1u;
+            const uint32_t ph = (g + t) & 1u;
             const uint32_t sK = st, pK = par;  // K(t+1), if any
             uint32_t sV = st, pV = par;        // V(t)
             if (has_next) ring_next(sV, pV);
@@ -469,6 +527,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               mbar_wait(p_ready(0), ph);
             }
             tc_fence_after();
+            FDM_WAIT_O_FREE(0, t)
             ok = false;
             trace_ev(p, tr, 2, 2, t);
             if (has_next) {
@@ -487,11 +546,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               issue_qk(1, stage_smem(sK), [&] { if (!ok) ok = mbar_test_wait(p_ready(1), ph); });
               commit(s_full(1));
               commit(kv_empty(sK));
+              if (PERSIST && !has_next2) commit(q_empty);   // that was the item's last QK^T
               trace_ev(p, tr, 3, 1, t);
             }
             // ---- PV_B(t) ----
             if (!ok) mbar_wait(p_ready(1), ph);
             tc_fence_after();
+            FDM_WAIT_O_FREE(1, t)
             ok = false;
             trace_ev(p, tr, 3, 2, t);
             if (has_next2) {
@@ -503,59 +564,66 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             commit(o_done(1));
             commit(kv_empty(sV));
             trace_ev(p, tr, 3, 3, t);
-            if (!has_next) break;
-            st = sK2;
+            st = sK2;   // the ring item after V(t) (and after K(t+1), if there was one)
             par = pK2;
+            ++t;
+            if (!has_next) break;
             j = jn;
             jn = jn2;
-            ++t;
           }
-        } else {
-        issue_qk(0, stage_addr(0), no_probe);
-        commit(s_full(0));
-        issue_qk(1, stage_addr(0), no_probe);
-        commit(s_full(1));
-        commit(kv_empty(0));
+          g += t;
+      } else {
+        // P is written back over S_X (TMEM) and feeds a TS MMA: PV_X(t) has to go before QK_X(t+1).
+        // Ring items: K(t), V(t) alternate.
         uint32_t t = 0;
-        // active tiles are numbered t = 0,1,...; K(t) is ring slot 2t, V(t) is ring slot 2t+1
         while (true) {
-          const int jn = next_active(j + 1);
           const bool has_next = jn < p.n_kv_tiles;
-          const uint32_t uV = 2 * t + 1, uKn = 2 * t + 2;
-          const uint32_t ph = t & 1u;
+          const int jn2 = has_next ? next_active(jn + 1) : jn;
+          const uint32_t ph = (g + t) & 1u;
+          const uint32_t sV = st, pV = par;   // V(t)
+          uint32_t sKn = st, pKn = par;       // K(t+1), if any
+          ring_next(sKn, pKn);
           // both operand tiles of this half-iteration were requested more than an iteration ago: take their
           // (already satisfied, but ~100-cycle) barrier waits BEFORE blocking on the softmax, so that PV_A
           // and QK_A go out back to back once P_A arrives
-          wait_full(uV);
-          if (has_next) wait_full(uKn);
+          mbar_wait(kv_full(sV), pV);
+          if (has_next) mbar_wait(kv_full(sKn), pKn);
           trace_ev(p, tr, 2, 0, t);
           mbar_wait(p_ready(0), ph);
           trace_ev(p, tr, 2, 1, t);
           tc_fence_after();
-          issue_pv(0, stage_addr(uV), t != 0, no_probe);
+          FDM_WAIT_O_FREE(0, t)
+          issue_pv(0, stage_smem(sV), t != 0, no_probe);
           trace_ev(p, tr, 2, 4, t);
           commit(o_done(0));
           if (has_next) {
             trace_ev(p, tr, 2, 5, t);
-            issue_qk(0, stage_addr(uKn), no_probe);
+            issue_qk(0, stage_smem(sKn), no_probe);
             commit(s_full(0));
           }
           trace_ev(p, tr, 2, 2, t);
           mbar_wait(p_ready(1), ph);
           trace_ev(p, tr, 2, 3, t);
           tc_fence_after();
-          issue_pv(1, stage_addr(uV), t != 0, no_probe);
+          FDM_WAIT_O_FREE(1, t)
+          issue_pv(1, stage_smem(sV), t != 0, no_probe);
           commit(o_done(1));
-          commit(kv_empty(uV % S::kStages));
-          if (!has_next) break;
-          issue_qk(1, stage_addr(uKn), no_probe);
-          commit(s_full(1));
-          commit(kv_empty(uKn % S::kStages));
-          j = jn;
+          commit(kv_empty(sV));
+          ring_next(st, par);
           ++t;
+          if (!has_next) break;
+          issue_qk(1, stage_smem(sKn), no_probe);
+          commit(s_full(1));
+          commit(kv_empty(sKn));
+          if (PERSIST && jn2 >= p.n_kv_tiles) commit(q_empty);   // that was the item's last QK^T
+          ring_next(st, par);
+          j = jn;
+          jn = jn2;
         }
-        }
+        g += t;
       }
+      } while (PERSIST && (++it, (item += n_clusters) < p.n_items));  // work items
+#undef FDM_WAIT_O_FREE
     }
     __syncwarp();
   }
@@ -565,7 +633,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int x = warp >> 2;              // Q tile of this warpgroup
     const int lane_group = warp & 3;      // TMEM lanes [32*lane_group, +32)
     const int row_in_tile = lane_group * 32 + lane;
-    const int row = q0 + x * kQTile + row_in_tile;  // global query index
     const uint32_t lane_off = (uint32_t)(lane_group * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + (uint32_t)(x * 128);
     const uint32_t tO = tmem_base + lane_off + 256u + (uint32_t)(x * 128);
@@ -573,21 +640,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // this thread's row of the K-major, 128B-swizzled P tile in shared memory (PS)
     const uint32_t p_row = base + S::kPOff + (uint32_t)x * S::kPBytes + (uint32_t)row_in_tile * 128u;
     const uint32_t p_sw = (uint32_t)(row_in_tile & 7);
+    uint32_t g = 0;   // KV tiles processed in earlier work items: the barrier phases count tiles across items
+    uint32_t it = 0;  // work items started
+    uint32_t item = cluster_id;
+      do {
     const int8_t* mask_row = nullptr;
-    if (has_mask) mask_row = mask_bh + (int64_t)min(row / p.mask_bq, p.nbq - 1) * p.nbk;
+    if (has_mask)
+      mask_row = mask_bh + (int64_t)min((item_q0(item) + x * kQTile + row_in_tile) / p.mask_bq, p.nbq - 1) * p.nbk;
 
     float m_run = -INFINITY;  // running max, scaled-log2 domain
     float l_run = 0.f;
-    uint32_t t = 0;
+    uint32_t t = 0;   // tiles of this item done
     for (int j = next_active(0); j < p.n_kv_tiles; j = next_active(j + 1)) {
       const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
       trace_ev(p, tr, x, 0, t);
-      mbar_wait(s_full(x), t & 1u);
+      mbar_wait(s_full(x), (g + t) & 1u);
       trace_ev(p, tr, x, 1, t);
       tc_fence_after();
       // PS: has PV_X(t-1) finished reading the P tile? Probed here, needed only at the first store of P
       bool p_free = !DEC || t == 0;
-      if (DEC && t > 0) p_free = mbar_test_wait(o_done(x), (t - 1) & 1u);
+      if (DEC && t > 0) p_free = mbar_test_wait(o_done(x), (g + t - 1) & 1u);
       const int valid = p.Sk - j * kKvTile;  // keys of this tile inside the sequence
       bool seg0 = true, seg1 = true;
       if (has_mask) {
@@ -611,7 +683,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           } else {
             mbar_arrive(s_free(x));
           }
-          if (!p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+          if (!p_free) mbar_wait(o_done(x), (g + t - 1) & 1u);
         }
         if (PS) {
 #pragma unroll
@@ -667,7 +739,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (t > 0) {
           // O_X may only be touched between PV_X(t-1) and PV_X(t)
           tmem_dirty = true;
-          mbar_wait(o_done(x), (t - 1) & 1u);
+          mbar_wait(o_done(x), (g + t - 1) & 1u);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < HD / 32; ++c) {
@@ -685,7 +757,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // LS: all exponentials of the tile are computed and packed into registers first (64 registers replace the 128 of
       // S as they are consumed) and the wait comes just before the burst of stores -- PV_X(t-1) has ~the whole softmax
       // of tile t to finish instead of its first third, so the single P buffer stops serialising PV(t-1) and exp(t).
-      if (!LS && DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+      if (!LS && DEC && !p_free) mbar_wait(o_done(x), (g + t - 1) & 1u);
       // ---- P = exp2(S*scale - m): over the first columns of S_X in TMEM, or into the P tile in smem ----
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
       const uint64_t scale2 = f2(p.scale_log2, p.scale_log2), negm2 = f2(neg_m, neg_m);
@@ -745,7 +817,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         compute(s2, pk2);
         compute(s3, pk3);
         trace_ev(p, tr, x, 7, t);
-        if (DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
+        if (DEC && !p_free) mbar_wait(o_done(x), (g + t - 1) & 1u);
         store(pk0, 0);
         store(pk1, 1);
         store(pk2, 2);
@@ -788,23 +860,39 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
     // ---- epilogue: O / l -> global ----
     if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 2] = clock64();
+    // (decoded here rather than before the tile loop: nothing of it stays live across the loop)
+    const int h = item_h(item), b = item_b(item);
+    const int row = item_q0(item) + x * kQTile + row_in_tile;  // global query index
     const bool row_ok = row < p.Sq;
     uint16_t* out_row = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ts + (int64_t)h * HD;
     if (t > 0) {
-      mbar_wait(o_done(x), (t - 1) & 1u);
+      mbar_wait(o_done(x), (g + t - 1) & 1u);
       tc_fence_after();
     }
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+    // the whole O row goes to registers first, so that O_X is handed back to the MMA warp (next item's first PV) before
+    // the conversions and the global stores
+    uint32_t o_acc[HD / 32][32];
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
-      uint32_t r[32];
       if (t > 0) {
-        tmem_ld_32x32(tO + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
+        tmem_ld_32x32(tO + (uint32_t)(c * 32), o_acc[c]);
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = 0u;
+        for (int i = 0; i < 32; ++i) o_acc[c][i] = 0u;
       }
+    }
+    if (t > 0) tmem_ld_wait();
+    tc_fence_before();
+    if (CG == 2) {
+      __syncwarp();
+      if (lane == 0) arrive_lead(o_free(x));
+    } else {
+      mbar_arrive(o_free(x));
+    }
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      const uint32_t(&r)[32] = o_acc[c];
       if (row_ok) {
         U128 o[4];
 #pragma unroll
@@ -823,6 +911,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
+    g += t;
+    } while (PERSIST && (++it, (item += n_clusters) < p.n_items));  // work items
   }
 
   if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 3] = clock64();
@@ -836,9 +926,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
+static int attn_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE>
 static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                         const AttnParams& p, cudaStream_t st) {
+                         const AttnParams& p_in, cudaStream_t st) {
   using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2, PS, CG>;
   static std::atomic<bool> attr_set[64];  // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
@@ -848,9 +942,18 @@ static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set[dev].store(true, std::memory_order_release);
   }
-  const unsigned nq = (unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile));
+  AttnParams p = p_in;
+  const int64_t nq = (p.Sq + 2 * kQTile - 1) / (2 * kQTile);
+  p.nqb = (int)((nq + CG - 1) / CG);   // whole CTA pairs
+  const int64_t items = (int64_t)p.nqb * p.H * p.B;
+  FDM_REQUIRE(items < (1LL << 31) / CG, "attn: too many query blocks");
+  p.n_items = (uint32_t)items;
+  // dense: persistent, one CTA (pair) per SM (pair); masked: one CTA (pair) per item
+  const int64_t slots = std::max(1, num_sms() / CG);
+  constexpr bool kPersist = (EMU & 128) != 0 && !MASKED;   // see PERSIST in the kernel
+  const int64_t clusters = kPersist ? std::min<int64_t>(items, slots) : items;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((nq + CG - 1) / CG * CG, (unsigned)p.H, (unsigned)p.B);  // whole CTA pairs
+  cfg.gridDim = kPersist ? dim3((unsigned)(clusters * CG), 1, 1) : dim3((unsigned)(p.nqb * CG), (unsigned)p.H, (unsigned)p.B);
   cfg.blockDim = dim3(kAttnThreads);
   cfg.dynamicSmemBytes = S::kTotal;
   cfg.stream = st;
@@ -869,27 +972,11 @@ static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 template <int HD, int DT, int EMU, bool PS, int CG>
 static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                          const AttnParams& p, cudaStream_t st) {
-  if (p.trace != nullptr) {
-    // the timeline build exists for the default dense bf16 hd-128 configurations only
-    if constexpr (HD == 128 && DT == kDtBF16 && (EMU & 63) == 4) {
-      if (p.mask == nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, false, true>(tq, tk, tv, p, st);
-    }
-  }
-  if constexpr (CG == 1) {  // block-sparse calls never take the CTA-pair kernel (attn_use_pair)
-    if (p.mask != nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, true, false>(tq, tk, tv, p, st);
-  } else if (p.mask != nullptr) {
-    set_error("attn: internal error, block mask routed to the CTA-pair kernel");
-    return FDM_ERR_UNSUPPORTED;
-  }
   return launch_attn_k<HD, DT, EMU, PS, CG, false, false>(tq, tk, tv, p, st);
 }
 
 // experiment knob: FDM_ATTN_CG=1 runs single CTAs (P in TMEM over S) instead of CTA pairs (P through shared
 // memory) for hd 128 with 16-bit operands
-static int attn_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
 static bool attn_pair_setting() {
   static int v = attn_env("FDM_ATTN_CG", 2);
   return v == 2;
@@ -919,26 +1006,15 @@ static int attn_emu_setting(int hd) {
   return hd == 128 ? 4 : 12;
 }
 
-// late store of P (see the softmax loop); FDM_ATTN_LS=0 restores the store-as-you-go order for experiments
-static bool attn_late_store() {
-  static const int v = attn_env("FDM_ATTN_LS", 1);
-  return v != 0;
-}
 
 template <int HD, int DT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, cudaStream_t st) {
   const int emu = attn_emu_setting(HD);
-  if (attn_late_store()) {
-    if (emu <= 0) return launch_attn_e<HD, DT, 64 + 0>(tq, tk, tv, p, st);
-    if (emu <= 4) return launch_attn_e<HD, DT, 64 + 4>(tq, tk, tv, p, st);
-    if (emu <= 8) return launch_attn_e<HD, DT, 64 + 8>(tq, tk, tv, p, st);
-    if (emu <= 12) return launch_attn_e<HD, DT, 64 + 12>(tq, tk, tv, p, st);
-    return launch_attn_e<HD, DT, 64 + 16>(tq, tk, tv, p, st);
-  }
-  if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st);
-  if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st);
-  return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st);
+  // template argument: exponentials per 32 on the FMA pipe | 64 (late store of P) | 128 (persistent)
+  if (emu <= 4) return launch_attn_e<HD, DT, 128 + 64 + 4>(tq, tk, tv, p, st);
+  if (emu <= 8) return launch_attn_e<HD, DT, 128 + 64 + 8>(tq, tk, tv, p, st);
+  return launch_attn_e<HD, DT, 128 + 64 + 12>(tq, tk, tv, p, st);
 }
 
 static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,
@@ -951,41 +1027,22 @@ static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S
                    dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+}  // namespace pst
 }  // namespace fdm
 
 using namespace fdm;
+using namespace fdm::pst;
 
-static long long* g_attn_trace = nullptr;
-extern "C" int fdm_debug_set_attn_trace(void* device_buffer) {
-  g_attn_trace = (long long*)device_buffer;  // 4 roles x 8 events x 64 tiles x int64, or NULL to disable
-  return FDM_OK;
-}
 
 namespace fdm {
-// csrc/attention_persistent.cu: the same arguments, dense calls only
-int attn_fwd_persistent(const void* q, const void* k, const void* v, void* o, const int8_t* block_mask, int64_t B,
-                        int64_t Sq, int64_t Sk, int H, int hd, int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts,
-                        int64_t v_bs, int64_t v_ts, int64_t o_bs, int64_t o_ts, int mask_bq, int mask_bk, float scale,
-                        int qkv_dtype, void* stream);
-// Dense calls with at most this many KV tiles go to the persistent kernel (FDM_ATTN_PERSIST_TILES; 0 = never): its
-// item loop hides the per-CTA set-up / first loads / epilogue (~10-20 us), which is most of a 4-tile CTA's life; on
-// longer calls this file's one-item kernel is faster (see the header of attention_persistent.cu).
-static int attn_persist_tiles() {
-  static const int v = attn_env("FDM_ATTN_PERSIST_TILES", 16);
-  return v;
-}
-}  // namespace fdm
-
-extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o,
+int attn_fwd_persistent(const void* q, const void* k, const void* v, void* o,
                             const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
                             int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
                             int64_t v_ts, int64_t o_bs, int64_t o_ts, int mask_bq, int mask_bk,
                             float scale, int qkv_dtype, void* stream) {
-  if (block_mask == nullptr && g_attn_trace == nullptr && Sk > 0 && (Sk + kKvTile - 1) / kKvTile <= attn_persist_tiles())
-    return attn_fwd_persistent(q, k, v, o, block_mask, B, Sq, Sk, H, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts,
-                               mask_bq, mask_bk, scale, qkv_dtype, stream);
   int rc = require_sm100();
   if (rc) return rc;
+  FDM_REQUIRE(block_mask == nullptr, "attn: the persistent kernel takes dense calls only");
   FDM_REQUIRE(B >= 0 && Sq >= 0 && Sk >= 0 && H > 0, "attn: bad shape");
   if (B == 0 || Sq == 0) return FDM_OK;
   FDM_REQUIRE(q && k && v && o, "attn: null pointer");
@@ -1031,8 +1088,7 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
     p.nbk = (int)((Sk + mask_bk - 1) / mask_bk);
   }
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.reserved = 0;
-  p.trace = g_attn_trace;
+  p.trace = nullptr;
   CUtensorMap tq, tk, tv;
   // batch stride of a single-batch tensor is irrelevant but must still be a legal stride
   if (B == 1) {
@@ -1054,3 +1110,4 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   if (hd == 128) return f16 ? launch_attn<128, kDtF16>(tq, tk, tv, p, st) : launch_attn<128, kDtBF16>(tq, tk, tv, p, st);
   return f16 ? launch_attn<64, kDtF16>(tq, tk, tv, p, st) : launch_attn<64, kDtBF16>(tq, tk, tv, p, st);
 }
+}  // namespace fdm
