@@ -38,6 +38,9 @@ SIGNATURES = {
                              c_int64, c_int64, c_int64, c_int, c_int,
                              c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64,
                              c_int, c_int, c_float, c_int, c_void_p]),
+    "fdm_attn_fwd_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p,
+                                     c_int64, c_int64, c_int, c_int, c_int64, c_int64, c_int64, c_int64,
+                                     c_int, c_int, c_float, c_int, c_void_p]),
     "fdm_debug_set_attn_trace": (c_int, [c_void_p]),
     "fdm_qk_norm_rope": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_int,
                                  c_int64, c_int64, c_int64, c_int64, c_int64, c_float, c_int, c_int, c_void_p]),

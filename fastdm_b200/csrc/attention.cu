@@ -73,6 +73,16 @@ struct AttnParams {
   long long* trace;  // debug: per-event clock64 stamps of CTA (0,0,0), or nullptr
 };
 
+// Extra kernel parameter of the SCATTER kernels (Ulysses): the epilogue writes each query row straight into the output
+// buffer of the rank that owns the row's token shard -- peer memory over NVLink -- instead of a local buffer that an
+// all-to-all then redistributes: row r goes to o_peer[r / rows_per_peer], row r % rows_per_peer, token stride o_ts.
+// A parameter of its own (and a kernel entry of its own) so that the ordinary kernels' parameter space, and with it
+// their generated code, stay exactly as measured.
+struct ScatterParams {
+  void* o_peer[8];
+  int rows_per_peer;
+};
+
 // debug timeline: trace[(role * 8 + event) * 64 + tile] = clock64(); role 0/1 = softmax warp 0 of
 // Q tile A/B, role 2 (and 3) = MMA thread(s). Only CTA (0,0,0) writes, only when a buffer was registered.
 constexpr int kTraceTiles = 64;
@@ -168,10 +178,9 @@ __device__ __forceinline__ void ex2_emulated_pair(uint64_t y, float& p0, float& 
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
 }
 
-template <int HD, int DT, int EMUX, bool PS, int CG, bool MASKED, bool TRACE>
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+template <int HD, int DT, int EMUX, bool PS, int CG, bool MASKED, bool TRACE, bool SCATTER>
+__device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const CUtensorMap& tmap_k, const CUtensorMap& tmap_v,
+                                              const AttnParams& p, const ScatterParams& sp) {
   constexpr int ES = DT == kDtE4M3 ? 1 : 2;  // operand element size
   constexpr bool F16 = DT == kDtF16;
   constexpr int EMU = EMUX & 63;           // exponentials per 32 that run on the FMA pipe
@@ -789,7 +798,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ---- epilogue: O / l -> global ----
     if (life) p.trace[(3 * 8 + 7) * kTraceTiles + 2] = clock64();
     const bool row_ok = row < p.Sq;
-    uint16_t* out_row = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ts + (int64_t)h * HD;
+    uint16_t* out_row;
+    if constexpr (SCATTER) {
+      // (batch 1) the row's owner and its row there; rows beyond Sq are never stored
+      const int dest = min(row / sp.rows_per_peer, 7);
+      out_row = reinterpret_cast<uint16_t*>(sp.o_peer[dest]) + (int64_t)(row - dest * sp.rows_per_peer) * p.o_ts + (int64_t)h * HD;
+    } else {
+      out_row = reinterpret_cast<uint16_t*>(p.o) + (int64_t)b * p.o_bs + (int64_t)row * p.o_ts + (int64_t)h * HD;
+    }
     if (t > 0) {
       mbar_wait(o_done(x), (t - 1) & 1u);
       tc_fence_after();
@@ -836,16 +852,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE>
+template <int HD, int DT, int EMUX, bool PS, int CG, bool MASKED, bool TRACE>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  attn_fwd_body<HD, DT, EMUX, PS, CG, MASKED, TRACE, false>(tmap_q, tmap_k, tmap_v, p, ScatterParams{});
+}
+template <int HD, int DT, int EMUX, bool PS, int CG, bool MASKED>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_fwd_scatter_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const AttnParams p, const ScatterParams sp) {
+  attn_fwd_body<HD, DT, EMUX, PS, CG, MASKED, false, true>(tmap_q, tmap_k, tmap_v, p, sp);
+}
+
+template <int HD, int DT, int EMU, bool PS, int CG, bool MASKED, bool TRACE, bool SCATTER = false>
 static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                         const AttnParams& p, cudaStream_t st) {
+                         const AttnParams& p, cudaStream_t st, const ScatterParams* sp = nullptr) {
   using S = AttnSmem<HD, DT == kDtE4M3 ? 1 : 2, PS, CG>;
   static std::atomic<bool> attr_set[64];  // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
-  auto kern = attn_fwd_kernel<HD, DT, EMU, PS, CG, MASKED, TRACE>;
   if (!attr_set[dev].load(std::memory_order_acquire)) {
-    FDM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    if constexpr (SCATTER)
+      FDM_CUDA(cudaFuncSetAttribute(attn_fwd_scatter_kernel<HD, DT, EMU, PS, CG, MASKED>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    else
+      FDM_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, DT, EMU, PS, CG, MASKED, TRACE>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set[dev].store(true, std::memory_order_release);
   }
   const unsigned nq = (unsigned)((p.Sq + 2 * kQTile - 1) / (2 * kQTile));
@@ -861,19 +894,33 @@ static int launch_attn_k(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FDM_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, p));
+  if constexpr (SCATTER)
+    FDM_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_scatter_kernel<HD, DT, EMU, PS, CG, MASKED>, tq, tk, tv, p, *sp));
+  else
+    FDM_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<HD, DT, EMU, PS, CG, MASKED, TRACE>, tq, tk, tv, p));
   FDM_LAUNCH_CHECK("attn_fwd kernel launch");
   return FDM_OK;
 }
 
 template <int HD, int DT, int EMU, bool PS, int CG>
 static int launch_attn_p(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                         const AttnParams& p, cudaStream_t st) {
+                         const AttnParams& p, cudaStream_t st, const ScatterParams* sp) {
   if (p.trace != nullptr) {
     // the timeline build exists for the default dense bf16 hd-128 configurations only
     if constexpr (HD == 128 && DT == kDtBF16 && (EMU & 63) == 4) {
       if (p.mask == nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, false, true>(tq, tk, tv, p, st);
     }
+  }
+  if (sp != nullptr) {
+    // epilogue scatters the rows to their owners' buffers (Ulysses): built for the Wan / Qwen case, hd 128, bf16
+    if constexpr (HD == 128 && DT == kDtBF16 && (EMU & 63) == 4) {
+      if constexpr (CG == 1) {
+        if (p.mask != nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, true, false, true>(tq, tk, tv, p, st, sp);
+      }
+      if (p.mask == nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, false, false, true>(tq, tk, tv, p, st, sp);
+    }
+    set_error("attn: the scattering epilogue is built for head_dim 128, bf16, default exp2 split");
+    return FDM_ERR_UNSUPPORTED;
   }
   if constexpr (CG == 1) {  // block-sparse calls never take the CTA-pair kernel (attn_use_pair)
     if (p.mask != nullptr) return launch_attn_k<HD, DT, EMU, PS, CG, true, false>(tq, tk, tv, p, st);
@@ -904,11 +951,11 @@ static bool attn_use_pair(int64_t Sq, int64_t Sk, bool masked) {
 }
 template <int HD, int DT, int EMU>
 static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                         const AttnParams& p, cudaStream_t st) {
+                         const AttnParams& p, cudaStream_t st, const ScatterParams* sp) {
   if constexpr (HD == 128 && DT != kDtE4M3) {
-    if (attn_use_pair(p.Sq, p.Sk, p.mask != nullptr)) return launch_attn_p<HD, DT, EMU, true, 2>(tq, tk, tv, p, st);
+    if (attn_use_pair(p.Sq, p.Sk, p.mask != nullptr)) return launch_attn_p<HD, DT, EMU, true, 2>(tq, tk, tv, p, st, sp);
   }
-  return launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st);
+  return launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st, sp);
 }
 
 // how many of every 32 exponentials run on the FMA pipe instead of MUFU (tuning knob; the default is
@@ -927,18 +974,18 @@ static bool attn_late_store() {
 
 template <int HD, int DT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                       const AttnParams& p, cudaStream_t st) {
+                       const AttnParams& p, cudaStream_t st, const ScatterParams* sp = nullptr) {
   const int emu = attn_emu_setting(HD);
   if (attn_late_store()) {
-    if (emu <= 0) return launch_attn_e<HD, DT, 64 + 0>(tq, tk, tv, p, st);
-    if (emu <= 4) return launch_attn_e<HD, DT, 64 + 4>(tq, tk, tv, p, st);
-    if (emu <= 8) return launch_attn_e<HD, DT, 64 + 8>(tq, tk, tv, p, st);
-    if (emu <= 12) return launch_attn_e<HD, DT, 64 + 12>(tq, tk, tv, p, st);
-    return launch_attn_e<HD, DT, 64 + 16>(tq, tk, tv, p, st);
+    if (emu <= 0) return launch_attn_e<HD, DT, 64 + 0>(tq, tk, tv, p, st, sp);
+    if (emu <= 4) return launch_attn_e<HD, DT, 64 + 4>(tq, tk, tv, p, st, sp);
+    if (emu <= 8) return launch_attn_e<HD, DT, 64 + 8>(tq, tk, tv, p, st, sp);
+    if (emu <= 12) return launch_attn_e<HD, DT, 64 + 12>(tq, tk, tv, p, st, sp);
+    return launch_attn_e<HD, DT, 64 + 16>(tq, tk, tv, p, st, sp);
   }
-  if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st);
-  if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st);
-  return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st);
+  if (emu <= 0) return launch_attn_e<HD, DT, 0>(tq, tk, tv, p, st, sp);
+  if (emu <= 4) return launch_attn_e<HD, DT, 4>(tq, tk, tv, p, st, sp);
+  return launch_attn_e<HD, DT, 8>(tq, tk, tv, p, st, sp);
 }
 
 static int make_qkv_tmap(CUtensorMap* out, const void* ptr, int64_t B, int64_t S, int H, int hd,
@@ -976,19 +1023,20 @@ static int attn_persist_tiles() {
 }
 }  // namespace fdm
 
-extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o,
-                            const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
-                            int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
-                            int64_t v_ts, int64_t o_bs, int64_t o_ts, int mask_bq, int mask_bk,
-                            float scale, int qkv_dtype, void* stream) {
-  if (block_mask == nullptr && g_attn_trace == nullptr && Sk > 0 && (Sk + kKvTile - 1) / kKvTile <= attn_persist_tiles())
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, void* const* o_peers, int n_peers,
+                         int64_t rows_per_peer, const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
+                         int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
+                         int64_t v_ts, int64_t o_bs, int64_t o_ts, int mask_bq, int mask_bk,
+                         float scale, int qkv_dtype, void* stream) {
+  if (o_peers == nullptr && block_mask == nullptr && g_attn_trace == nullptr && Sk > 0 &&
+      (Sk + kKvTile - 1) / kKvTile <= attn_persist_tiles())
     return attn_fwd_persistent(q, k, v, o, block_mask, B, Sq, Sk, H, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts,
                                mask_bq, mask_bk, scale, qkv_dtype, stream);
   int rc = require_sm100();
   if (rc) return rc;
   FDM_REQUIRE(B >= 0 && Sq >= 0 && Sk >= 0 && H > 0, "attn: bad shape");
   if (B == 0 || Sq == 0) return FDM_OK;
-  FDM_REQUIRE(q && k && v && o, "attn: null pointer");
+  FDM_REQUIRE(q && k && v && (o || o_peers), "attn: null pointer");
   FDM_REQUIRE(hd == 64 || hd == 128, "attn: head_dim %d unsupported (64 or 128)", hd);
   FDM_REQUIRE(qkv_dtype == FDM_BF16 || qkv_dtype == FDM_F16 || qkv_dtype == FDM_E4M3,
               "attn: q/k/v dtype must be bf16, f16 or e4m3");
@@ -1033,6 +1081,22 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   p.scale_log2 = scale * 1.4426950408889634f;
   p.reserved = 0;
   p.trace = g_attn_trace;
+  ScatterParams sc;
+  sc.rows_per_peer = 0;
+  for (int i = 0; i < 8; ++i) sc.o_peer[i] = nullptr;
+  if (o_peers != nullptr) {
+    FDM_REQUIRE(B == 1 && n_peers >= 1 && n_peers <= 8 && rows_per_peer > 0 && rows_per_peer * n_peers >= Sq &&
+                    rows_per_peer < (1LL << 31),
+                "attn: scatter needs batch 1, 1..8 peers and rows_per_peer * peers >= Sq");
+    for (int i = 0; i < n_peers; ++i) {
+      FDM_REQUIRE(o_peers[i] != nullptr && (uintptr_t)o_peers[i] % 16 == 0, "attn: peer output pointers must be 16-byte aligned");
+      sc.o_peer[i] = o_peers[i];
+      p.o_vec32 = p.o_vec32 && ((uintptr_t)o_peers[i] % 32 == 0);
+    }
+    for (int i = n_peers; i < 8; ++i) sc.o_peer[i] = o_peers[n_peers - 1];
+    sc.rows_per_peer = (int)rows_per_peer;
+  }
+  const ScatterParams* sp = o_peers != nullptr ? &sc : nullptr;
   CUtensorMap tq, tk, tv;
   // batch stride of a single-batch tensor is irrelevant but must still be a legal stride
   if (B == 1) {
@@ -1049,8 +1113,26 @@ extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o
   rc = make_qkv_tmap(&tv, v, B, Sk, H, hd, v_bs, v_ts, es);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (qkv_dtype == FDM_E4M3) return launch_attn<128, kDtE4M3>(tq, tk, tv, p, st);
+  if (qkv_dtype == FDM_E4M3) return launch_attn<128, kDtE4M3>(tq, tk, tv, p, st, sp);
   const bool f16 = qkv_dtype == FDM_F16;
-  if (hd == 128) return f16 ? launch_attn<128, kDtF16>(tq, tk, tv, p, st) : launch_attn<128, kDtBF16>(tq, tk, tv, p, st);
-  return f16 ? launch_attn<64, kDtF16>(tq, tk, tv, p, st) : launch_attn<64, kDtBF16>(tq, tk, tv, p, st);
+  if (hd == 128) return f16 ? launch_attn<128, kDtF16>(tq, tk, tv, p, st, sp) : launch_attn<128, kDtBF16>(tq, tk, tv, p, st, sp);
+  return f16 ? launch_attn<64, kDtF16>(tq, tk, tv, p, st, sp) : launch_attn<64, kDtBF16>(tq, tk, tv, p, st, sp);
+}
+
+extern "C" int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o,
+                            const int8_t* block_mask, int64_t B, int64_t Sq, int64_t Sk, int H, int hd,
+                            int64_t q_bs, int64_t q_ts, int64_t k_bs, int64_t k_ts, int64_t v_bs,
+                            int64_t v_ts, int64_t o_bs, int64_t o_ts, int mask_bq, int mask_bk,
+                            float scale, int qkv_dtype, void* stream) {
+  return attn_fwd_impl(q, k, v, o, nullptr, 0, 0, block_mask, B, Sq, Sk, H, hd, q_bs, q_ts, k_bs, k_ts, v_bs, v_ts, o_bs, o_ts,
+                       mask_bq, mask_bk, scale, qkv_dtype, stream);
+}
+
+extern "C" int fdm_attn_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_peers, int n_peers,
+                                    int64_t rows_per_peer, const int8_t* block_mask, int64_t Sq, int64_t Sk, int H, int hd,
+                                    int64_t q_ts, int64_t k_ts, int64_t v_ts, int64_t o_ts, int mask_bq, int mask_bk,
+                                    float scale, int qkv_dtype, void* stream) {
+  FDM_REQUIRE(o_peers != nullptr && n_peers >= 1, "attn: scatter needs the peers' output pointers");
+  return attn_fwd_impl(q, k, v, o_peers[0], o_peers, n_peers, rows_per_peer, block_mask, 1, Sq, Sk, H, hd, Sq * q_ts, q_ts,
+                       Sk * k_ts, k_ts, Sk * v_ts, v_ts, rows_per_peer * o_ts, o_ts, mask_bq, mask_bk, scale, qkv_dtype, stream);
 }

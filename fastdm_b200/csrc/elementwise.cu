@@ -752,6 +752,77 @@ __global__ void __launch_bounds__(256) qk_norm_rope_head_kernel(
   }
 }
 
+// Per-head norm + RoPE, bf16, second edition. The kernel above spends two thirds of its ~19 instructions per element
+// on bookkeeping -- a division per (token, head) row to find its token, q-or-k selects on weights and offsets, the
+// cos / sin pairs re-read and re-shuffled for every head although they only depend on the token -- and is issue-bound
+// at half of HBM speed. Here a LANES-wide group owns (token, q | k, chunk of 8 heads): q / k is blockIdx.y (uniform),
+// the token comes from one division per group, the weights and the rotation factors {c, c} / {-s, +s} are prepared once
+// and reused for the chunk's heads, which are 256 contiguous bytes apart. Same packed bf16 arithmetic (bit-identical).
+template <int LANES>
+__global__ void __launch_bounds__(256) qk_norm_rope_token_kernel(
+    __nv_bfloat16* __restrict__ buf, const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wk,
+    const __nv_bfloat16* __restrict__ cs, int tokens, int q_heads, int k_heads, int head_size, int64_t token_stride,
+    int64_t q_offset, int64_t k_offset, int64_t pos0, int64_t cs_stride, float eps, int heads_per_chunk) {
+  using T = __nv_bfloat16;
+  const bool isk = blockIdx.y != 0;
+  const int heads = isk ? k_heads : q_heads;
+  const T* w = isk ? wk : wq;
+  const int n_chunks = (heads + heads_per_chunk - 1) / heads_per_chunk;
+  const int li = threadIdx.x % LANES;
+  const int unit = blockIdx.x * (256 / LANES) + threadIdx.x / LANES;
+  const int tok = unit / n_chunks;
+  // (groups past the end keep running on the last unit so that the sub-warp shuffles stay well defined; they store nothing)
+  const bool live = heads > 0 && tok < tokens;
+  const int tok_c = live ? tok : 0;
+  const int h0 = live ? (unit - tok * n_chunks) * heads_per_chunk : 0;
+  const int h1 = live ? min(h0 + heads_per_chunk, heads) : 0;
+  T* base = buf + (int64_t)tok_c * token_stride + (isk ? k_offset : q_offset) + li * 8;
+  const U128 w_raw = w ? ldg128(w + li * 8) : U128{0u, 0u, 0u, 0u};
+  uint32_t cc[4], ss[4];
+  if (cs != nullptr) {
+    const T* crow = cs + (pos0 + tok_c) * cs_stride;
+    const uint2 craw = *reinterpret_cast<const uint2*>(crow + li * 4);
+    const uint2 sraw = *reinterpret_cast<const uint2*>(crow + (head_size >> 1) + li * 4);
+    const uint32_t cw[2] = {craw.x, craw.y}, sw[2] = {sraw.x, sraw.y};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t sel = (q & 1) ? 0x3232u : 0x1010u;                  // duplicate the high / low bf16
+      cc[q] = __byte_perm(cw[q >> 1], 0u, sel);                          // { c,  c}
+      ss[q] = __byte_perm(sw[q >> 1], 0u, sel) ^ 0x00008000u;            // {-s, +s}
+    }
+  }
+  const float inv_cols = 1.0f / (float)head_size;
+  constexpr int UNROLL = 4;
+  // (the trip count is the same for every group of a warp -- the reduction shuffles are warp-wide instructions)
+  for (int hb = h0; hb < h0 + heads_per_chunk; hb += UNROLL) {
+    U128 raw[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u)
+      raw[u] = (hb + u < h1) ? ldg128(base + (int64_t)(hb + u) * head_size) : U128{0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      uint32_t xp[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+      if (w != nullptr) {
+        float f[8];
+        unpack8<T>(raw[u], f);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sq += f[j] * f[j];
+        sq = warp_sum<LANES>(sq);
+        norm_scale8_bf16(f, rsqrtf(sq * inv_cols + eps), w_raw, xp);
+      }
+      if (cs != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t xs = __byte_perm(xp[q], 0u, 0x1032u);           // {x_2q+1, x_2q}
+          xp[q] = badd2(bmul2(xp[q], cc[q]), bmul2(xs, ss[q]));
+        }
+      }
+      if (hb + u < h1) stg128(base + (int64_t)(hb + u) * head_size, U128{xp[0], xp[1], xp[2], xp[3]});
+    }
+  }
+}
+
 // across-heads norm (Wan): one CTA per (token, q|k); the heads*head_size row lives in registers
 template <typename T, int VPT>
 __global__ void __launch_bounds__(512) qk_norm_rope_row_kernel(
@@ -1466,7 +1537,21 @@ int fdm_qk_norm_rope(void* buf, const void* wq, const void* wk, const void* cos_
     int64_t want = ((rows + rpw - 1) / rpw + 8 * 4 - 1) / (8 * 4);
     if (want < 1) want = 1;
     const unsigned g = (unsigned)want;
-    if (dtype == FDM_BF16) {
+    static const bool token_kernel = [] { const char* e = getenv("FDM_QKNR_TOKEN"); return e == nullptr || atoi(e) != 0; }();
+    if (dtype == FDM_BF16 && token_kernel && tokens < (1LL << 24)) {
+      const int hpc = 8;   // heads per group: the token's rotation factors are prepared once per 8 heads
+      const int max_heads = q_heads > k_heads ? q_heads : k_heads;
+      const int64_t units = tokens * ((max_heads + hpc - 1) / hpc);
+#define QKNR_TOKEN(L)                                                                                                  \
+  qk_norm_rope_token_kernel<L><<<dim3((unsigned)((units + 256 / L - 1) / (256 / L)), 2), 256, 0, st>>>(                \
+      (__nv_bfloat16*)buf, (const __nv_bfloat16*)wq, (const __nv_bfloat16*)wk, (const __nv_bfloat16*)cos_sin, (int)tokens, \
+      q_heads, k_heads, head_size, token_stride, q_offset, k_offset, pos0, cs_row_stride, eps, hpc)
+      if (lanes == 4) QKNR_TOKEN(4);
+      else if (lanes == 8) QKNR_TOKEN(8);
+      else if (lanes == 16) QKNR_TOKEN(16);
+      else QKNR_TOKEN(32);
+#undef QKNR_TOKEN
+    } else if (dtype == FDM_BF16) {
       if (lanes == 4) QKNR_HEAD(__nv_bfloat16, 4);
       else if (lanes == 8) QKNR_HEAD(__nv_bfloat16, 8);
       else if (lanes == 16) QKNR_HEAD(__nv_bfloat16, 16);

@@ -1,5 +1,11 @@
 // Host-side TMA descriptor encoding. cuTensorMapEncodeTiled is resolved through
 // cudaGetDriverEntryPoint so the library does not link against libcuda.
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "sm100.cuh"
 
 namespace fdm {
@@ -17,9 +23,69 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+// Descriptors are cached per (base, shape, strides, box, type, swizzle, promotion): a denoising loop calls every GEMM
+// and attention with the same buffers step after step (the caching allocator hands the same blocks back), and the driver
+// call costs more than the rest of a launch. The descriptor only encodes those values, so a hit is exact by
+// construction; a stale entry cannot exist. Bounded: the table is dropped when it reaches 8192 entries.
+namespace {
+struct TmapKey {
+  uint64_t v[16];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) {
+      h ^= x;
+      h *= 1099511628211ull;
+      h ^= h >> 29;
+    }
+    return (size_t)h;
+  }
+};
+std::mutex g_tmap_mutex;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+}  // namespace
+
+static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
+                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                       CUtensorMapSwizzle swz, CUtensorMapL2promotion l2);
+
 int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
               const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
               CUtensorMapSwizzle swz, CUtensorMapL2promotion l2) {
+  static const bool cache_on = [] { const char* e = getenv("FDM_TMAP_CACHE"); return e == nullptr || atoi(e) != 0; }();
+  if (!cache_on || rank > 5) return encode_tmap(out, dt, rank, base, dims, strides_bytes, box, swz, l2);
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  int dev = 0;
+  cudaGetDevice(&dev);
+  key.v[0] = (uint64_t)(uintptr_t)base;
+  key.v[1] = (uint64_t)dt | ((uint64_t)rank << 8) | ((uint64_t)swz << 16) | ((uint64_t)l2 << 24) | ((uint64_t)dev << 32);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[7 + i] = (uint64_t)box[i] | (i > 0 ? strides_bytes[i - 1] << 16 : 0ull);
+  }
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *out = it->second;
+      return FDM_OK;
+    }
+  }
+  const int rc = encode_tmap(out, dt, rank, base, dims, strides_bytes, box, swz, l2);
+  if (rc == FDM_OK) {
+    std::lock_guard<std::mutex> lock(g_tmap_mutex);
+    if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+  }
+  return rc;
+}
+
+static int encode_tmap(CUtensorMap* out, CUtensorMapDataType dt, int rank, const void* base,
+                       const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                       CUtensorMapSwizzle swz, CUtensorMapL2promotion l2) {
   PFN_encodeTiled enc = get_encode_tiled();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the CUDA driver");

@@ -9,6 +9,8 @@ FastDM's kernel registry (see fastdm_b200/integration.py).
 """
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib
@@ -18,6 +20,30 @@ _DT = {torch.bfloat16: FDM_BF16, torch.float16: FDM_F16, torch.float32: FDM_F32,
        torch.float8_e4m3fn: FDM_E4M3, torch.int8: FDM_S8}
 _ACT = {None: ACT_NONE, "none": ACT_NONE, "gelu_tanh": ACT_GELU_TANH, "gelu-approximate": ACT_GELU_TANH,
         "gelu_erf": ACT_GELU_ERF, "gelu": ACT_GELU_ERF}
+
+
+class _Ops:
+    """`_ops.<name>` for traced / compiled code, the op's Python body directly otherwise: the
+    dispatcher round trip of a `torch.library.custom_op` costs ~30 us per call, more than most of these kernels run
+    for on the text streams (a Qwen-Image step issues 1100 of them). FDM_OPS_DISPATCH=1 forces the dispatcher."""
+
+    def __init__(self):
+        self._direct = {}
+        self._always_dispatch = os.environ.get("FDM_OPS_DISPATCH", "0") == "1"
+
+    def register(self, name, custom_op_def):
+        self._direct[name] = custom_op_def._init_fn
+
+    def __getattr__(self, name):
+        if self._always_dispatch or torch.compiler.is_compiling():
+            return getattr(torch.ops.fastdm_b200, name)
+        try:
+            return self._direct[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+
+_ops = _Ops()
 
 
 def _dt(t: torch.Tensor, what: str) -> int:
@@ -330,8 +356,51 @@ def attention(query, key, value, num_heads, head_dim, scale=None, block_mask=Non
         scale = head_dim ** -0.5
     if out is None:
         out = torch.empty(query.shape, device=query.device, dtype=_attn_out_dtype(query.dtype))
-    torch.ops.fastdm_b200.attn_fwd_(out, query, key, value, num_heads, head_dim, scale, block_mask, mask_bq, mask_bk)
+    _ops.attn_fwd_(out, query, key, value, num_heads, head_dim, scale, block_mask, mask_bq, mask_bk)
     return out
+
+
+def attention_scatter(query, key, value, num_heads, head_dim, peer_ptrs, rows_per_peer, out_token_stride, scale=None,
+                      block_mask=None, mask_bq=128, mask_bk=64):
+    """Attention whose epilogue writes query row r into the buffer of the rank that owns it (Ulysses):
+    peer_ptrs[r // rows_per_peer] + (r % rows_per_peer) * out_token_stride elements. `peer_ptrs` are device addresses
+    (ints) of the peers' output buffers mapped into this process, already offset to this rank's head columns.
+    Nothing is returned: the caller owns the buffers and the cross-rank ordering (fdm_attn_fwd_scatter)."""
+    what = "attention_scatter"
+    _cuda(query, what)
+    if query.ndim != 3 or query.shape[0] != 1 or key.shape[0] != 1 or value.shape[0] != 1:
+        raise RuntimeError(f"fastdm_b200.{what}: q/k/v must be [1, seq, heads*head_dim]")
+    if not (query.dtype == key.dtype == value.dtype == torch.bfloat16) or head_dim != 128:
+        raise RuntimeError(f"fastdm_b200.{what}: built for bf16, head_dim 128")
+    _, sq, c = query.shape
+    sk = key.shape[1]
+    if c != num_heads * head_dim or key.shape[2] != c or value.shape[2] != c or value.shape[1] != sk:
+        raise RuntimeError(f"fastdm_b200.{what}: shape mismatch")
+    n = len(peer_ptrs)
+    if not 1 <= n <= 8 or rows_per_peer * n < sq:
+        raise RuntimeError(f"fastdm_b200.{what}: need 1..8 peers covering all {sq} query rows")
+    ts = []
+    for t in (query, key, value):
+        if t.stride(2) != 1 or (t.stride(1) * t.element_size()) % 16 or t.data_ptr() % 16:
+            t = t.contiguous()
+        ts.append(t)
+    q, k, v = ts
+    if block_mask is not None:
+        block_mask = block_mask.to(torch.int8)
+        nbq, nbk = -(-sq // mask_bq), -(-sk // mask_bk)
+        if tuple(block_mask.shape) != (1, num_heads, nbq, nbk):
+            raise RuntimeError(f"fastdm_b200.{what}: sparse_mask must be {(1, num_heads, nbq, nbk)}")
+        block_mask = block_mask.contiguous()
+    import ctypes
+    arr = (ctypes.c_void_p * n)(*[int(p) for p in peer_ptrs])
+    if scale is None:
+        scale = head_dim ** -0.5
+    with torch.cuda.device(query.device):
+        rc = _lib.load().fdm_attn_fwd_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), arr, n, int(rows_per_peer),
+                                              _ptr(block_mask), sq, sk, num_heads, head_dim, q.stride(1), k.stride(1),
+                                              v.stride(1), int(out_token_stride), mask_bq, mask_bk, float(scale),
+                                              _dt(q, what), _stream(q))
+    _lib.check(rc, what)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -373,7 +442,7 @@ def qk_norm_rope_(buf, wq, wk, cos_sin, q_heads, k_heads, head_size, q_offset=0,
     and the interleaved rotary embedding, bit-identical to rms_norm + rotary_pos_embedding."""
     if k_offset is None:
         k_offset = q_offset + q_heads * head_size
-    torch.ops.fastdm_b200.qk_norm_rope_(buf, wq, wk, cos_sin, q_heads, k_heads, head_size, q_offset, k_offset, pos0,
+    _ops.qk_norm_rope_(buf, wq, wk, cos_sin, q_heads, k_heads, head_size, q_offset, k_offset, pos0,
                                         eps, across_heads)
 
 
@@ -430,7 +499,7 @@ def layernorm_modulate_quant(x, mul, add, rows_per_batch, quant_dtype, eps=1e-6,
     """LayerNorm(x) * mul + add (no affine LN) followed by the per-token quantisation the next
     QLinear would do. Returns (codes, scales, azp-or-None, y-or-None)."""
     code = {torch.float8_e4m3fn: FDM_E4M3, torch.int8: FDM_S8, None: FDM_BF16}[quant_dtype]
-    q, s, zp, y = torch.ops.fastdm_b200.layernorm_modulate_quant(x, mul, add, rows_per_batch, eps, round_steps, code,
+    q, s, zp, y = _ops.layernorm_modulate_quant(x, mul, add, rows_per_batch, eps, round_steps, code,
                                                                  want_y or quant_dtype is None)
     return (q if quant_dtype is not None else None, s if quant_dtype is not None else None,
             zp if quant_dtype == torch.int8 else None, y if (want_y or quant_dtype is None) else None)
@@ -490,6 +559,18 @@ def rel_l1_sums(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_ops.register("quant_fp8", _quant_fp8)
+_ops.register("quant_int8", _quant_int8)
+_ops.register("rms_norm", _rms_norm)
+_ops.register("rope_", _rope)
+_ops.register("gelu_and_mul", _gelu_and_mul)
+_ops.register("gemm_fp8_", _gemm_fp8)
+_ops.register("gemm_int8_", _gemm_int8)
+_ops.register("attn_fwd_", _attn_fwd)
+_ops.register("qk_norm_rope_", _qk_norm_rope)
+_ops.register("layernorm_modulate_quant", _ln_mod_quant)
+
+
 # ================================================================================================
 # Public op API -- same names and signatures as fastdm/kernel/operators_set.py (reference)
 # ================================================================================================
@@ -501,32 +582,32 @@ def rms_norm(input: torch.Tensor, scale: Optional[torch.Tensor], eps: float) -> 
     input dtype with the weight cast to it and the result is returned in the weight's dtype -- same dtype contract,
     values within one rounding of the input dtype."""
     if scale is not None and scale.dtype != input.dtype:
-        return torch.ops.fastdm_b200.rms_norm(input, scale.to(input.dtype), eps).to(scale.dtype)
-    return torch.ops.fastdm_b200.rms_norm(input, scale, eps)
+        return _ops.rms_norm(input, scale.to(input.dtype), eps).to(scale.dtype)
+    return _ops.rms_norm(input, scale, eps)
 
 
 def rotary_pos_embedding(query: torch.Tensor, key: torch.Tensor, head_size: int, cos_sin_cache: torch.Tensor,
                          is_neox: bool = False):
     """operators_set.py:23-52; in place on query and key, returns None (kernel/torch/rotemb.py:62-64)."""
-    torch.ops.fastdm_b200.rope_(query, key, head_size, cos_sin_cache, is_neox)
+    _ops.rope_(query, key, head_size, cos_sin_cache, is_neox)
     return
 
 
 def gelu_and_mul(input: torch.Tensor) -> torch.Tensor:
     """operators_set.py:54-67: x[..., :d] * gelu(x[..., d:])."""
-    return torch.ops.fastdm_b200.gelu_and_mul(input)
+    return _ops.gelu_and_mul(input)
 
 
 def quantize_to_int8(input: torch.Tensor, symmetric: bool = True
                      ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
     """operators_set.py:69-84; returns (int8 codes, scales [M,1], azp [M,1] int32 or None)."""
-    q, s, zp = torch.ops.fastdm_b200.quant_int8(input, symmetric, ACT_NONE)
+    q, s, zp = _ops.quant_int8(input, symmetric, ACT_NONE)
     return q, s, (None if symmetric else zp)
 
 
 def quantize_to_fp8(input: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """operators_set.py:86-100; returns (e4m3 codes, scales [M,1])."""
-    return torch.ops.fastdm_b200.quant_fp8(input, ACT_NONE)
+    return _ops.quant_fp8(input, ACT_NONE)
 
 
 def fp8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b: torch.Tensor,
@@ -541,7 +622,7 @@ def fp8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b:
         raise AssertionError("fp8_matmul: K and N must be multiples of 16")
     if out is None:
         out = torch.empty((a.shape[0], b.shape[1]), device=a.device, dtype=out_dtype)
-    torch.ops.fastdm_b200.gemm_fp8_(out, a, b, scale_a, scale_b, bias, _ACT[act], gate, residual, rows_per_batch,
+    _ops.gemm_fp8_(out, a, b, scale_a, scale_b, bias, _ACT[act], gate, residual, rows_per_batch,
                                     round_steps)
     return out
 
@@ -557,7 +638,7 @@ def int8_matmul(a: torch.Tensor, b: torch.Tensor, scale_a: torch.Tensor, scale_b
         raise AssertionError("int8_matmul: K and N must be multiples of 16")
     if out is None:
         out = torch.empty((a.shape[0], b.shape[1]), device=a.device, dtype=out_dtype)
-    torch.ops.fastdm_b200.gemm_int8_(out, a, b, scale_a, scale_b, azp_adj, azp, bias, _ACT[act], gate, residual,
+    _ops.gemm_int8_(out, a, b, scale_a, scale_b, azp_adj, azp, bias, _ACT[act], gate, residual,
                                      rows_per_batch, round_steps)
     return out
 
@@ -593,9 +674,9 @@ def sparse_scaled_dot_product_attention(query: torch.Tensor, key: torch.Tensor, 
 # fused extras used by the host-side layers (fastdm_b200/layers.py)
 def gelu_quantize_to_fp8(input: torch.Tensor, approximate: str = "tanh"):
     """quantize_to_fp8(F.gelu(x, approximate=...)) in one pass over HBM."""
-    return torch.ops.fastdm_b200.quant_fp8(input, ACT_GELU_TANH if approximate == "tanh" else ACT_GELU_ERF)
+    return _ops.quant_fp8(input, ACT_GELU_TANH if approximate == "tanh" else ACT_GELU_ERF)
 
 
 def gelu_quantize_to_int8(input: torch.Tensor, approximate: str = "tanh"):
     """quantize_to_int8(F.gelu(x, approximate=...), symmetric=False) in one pass over HBM."""
-    return torch.ops.fastdm_b200.quant_int8(input, False, ACT_GELU_TANH if approximate == "tanh" else ACT_GELU_ERF)
+    return _ops.quant_int8(input, False, ACT_GELU_TANH if approximate == "tanh" else ACT_GELU_ERF)

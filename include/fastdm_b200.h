@@ -211,6 +211,18 @@ int fdm_attn_fwd(const void* q, const void* k, const void* v, void* o, const int
 /* Debug aid (not part of the reference API): register a device buffer of 4*8*64 int64 that CTA
  * (0,0,0) of every following fdm_attn_fwd launch fills with clock64() stamps of its pipeline events
  * (tools/attn_trace.py prints the timeline); NULL disables it. */
+/* fdm_attn_fwd whose epilogue SCATTERS the output rows to their owners (Ulysses sequence parallelism, no reference
+ * counterpart): query row r is written to o_peers[r / rows_per_peer], row r % rows_per_peer, token stride o_ts -- each
+ * pointer is the (peer-mapped, e.g. CUDA VMM / torch symmetric memory) address of that rank's [rows_per_peer, >= H*hd]
+ * output buffer, already offset to this rank's head columns. The post-attention all-to-all and its unpack pass
+ * disappear: the transfer is the kernel's own stores over NVLink, overlapped with the other CTAs' math. The caller
+ * orders the peers' reads after every rank's launch (a cross-rank barrier on the stream). o_peers is a HOST array of
+ * n_peers (<= 8) device pointers. Batch 1, head_dim 128, bf16; dense or block-sparse. */
+int fdm_attn_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_peers, int n_peers,
+                         int64_t rows_per_peer, const int8_t* block_mask, int64_t Sq, int64_t Sk, int H, int hd,
+                         int64_t q_ts, int64_t k_ts, int64_t v_ts, int64_t o_ts, int mask_bq, int mask_bk,
+                         float scale, int qkv_dtype, void* stream);
+
 int fdm_debug_set_attn_trace(void* device_buffer);
 
 /* ---------------------------------------------------------------------------------------------

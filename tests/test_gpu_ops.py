@@ -504,6 +504,34 @@ def test_sparse_attention_floor_sized_mask_is_padded_with_ones(ops):
                                                 block_q=bq, block_k=bk)
 
 
+@pytest.mark.parametrize("shape", [(1000, 1500, 2, 3), (2304, 2304, 3, 4), (700, 640, 1, 2)])
+@pytest.mark.parametrize("masked", [False, True])
+def test_attention_scatter_epilogue_equals_plain_attention(ops, shape, masked):
+    """fdm_attn_fwd_scatter (Ulysses): query row r lands in buffer r // rows_per_peer at row r % rows_per_peer, in the
+    caller's head columns, bit-identical to the plain kernel's output; here the "peers" are slices of one local tensor.
+    Covers the CTA-pair kernel (Sk >= 1024, dense), the single-CTA kernel (short Sk, block mask) and a ragged last peer."""
+    sq, sk, h, peers = shape
+    hd, H_total = 128, 2 * h            # the owners' buffers hold twice our heads: we write the second half of the columns
+    g = torch.Generator(device=DEV).manual_seed(sq + sk)
+    q = torch.randn(1, sq, h * hd, device=DEV, generator=g).to(BF)
+    k = torch.randn(1, sk, h * hd, device=DEV, generator=g).to(BF)
+    v = torch.randn(1, sk, h * hd, device=DEV, generator=g).to(BF)
+    mask = None
+    if masked:
+        mask = (torch.rand(1, h, -(-sq // 128), -(-sk // 64), device=DEV, generator=g) < 0.6).to(torch.int8)
+        mask[..., 0] = 1
+    rows = -(-sq // peers)               # ragged: the last peer receives fewer rows
+    bufs = torch.full((peers, rows, H_total * hd), 7.0, device=DEV, dtype=BF)
+    ptrs = [bufs[i].data_ptr() + h * hd * 2 for i in range(peers)]
+    ops.attention_scatter(q, k, v, h, hd, ptrs, rows, H_total * hd, hd ** -0.5, mask)
+    want = ops.attention(q, k, v, h, hd, hd ** -0.5, mask)[0]
+    got = bufs[:, :, h * hd:].reshape(peers * rows, h * hd)[:sq]
+    assert torch.equal(got, want)
+    assert float(bufs[:, :, : h * hd].min()) == 7.0 and float(bufs[:, :, : h * hd].max()) == 7.0     # other columns untouched
+    if peers * rows > sq:
+        assert float(bufs.reshape(peers * rows, -1)[sq:].min()) == 7.0                                  # rows past Sq untouched
+
+
 def test_sparse_attention_all_ones_equals_dense(ops):
     # the reference's only sparse test: tests/test_sparge_attention.py:81 (mask = ones)
     torch.manual_seed(0)

@@ -179,6 +179,19 @@ def attn_perf():
             print("   torch sdpa failed:", str(e)[:200])
         print(f"attn b{b} sq{sq} sk{sk} h{h} hd{hd}: {ms:.3f} ms {fl/ms/1e9:.0f} TF | torch sdpa {ms_t:.3f} ms {fl/ms_t/1e9:.0f} TF")
         res[f"{b}x{sq}x{sk}x{h}x{hd}"] = dict(ms=ms, tflops=fl / ms / 1e9, torch_ms=ms_t, torch_tflops=fl / ms_t / 1e9)
+    # fp8 (e4m3 q/k/v, P quantised to e4m3, f32 accumulate; hd 128): TFLOP/s and error against the bf16 kernel
+    for (b, sq, sk, h, hd) in ((1, 8704, 8704, 24, 128), (1, 80640, 80640, 4, 128)):
+        q = torch.randn(b, sq, h * hd, device=DEV, dtype=BF)
+        k = torch.randn(b, sk, h * hd, device=DEV, dtype=BF)
+        v = torch.randn(b, sk, h * hd, device=DEV, dtype=BF)
+        q8, k8, v8 = (t.to(torch.float8_e4m3fn) for t in (q, k, v))
+        ms = timeit(lambda: ops.attention(q8, k8, v8, h, hd), iters=5, warm=2)
+        fl = 4.0 * b * h * sq * sk * hd
+        y8 = ops.attention(q8, k8, v8, h, hd).float()
+        y16 = ops.attention(q, k, v, h, hd).float()
+        cos = torch.nn.functional.cosine_similarity(y8.flatten(), y16.flatten(), dim=0).item()
+        print(f"attn fp8 b{b} sq{sq} sk{sk} h{h} hd{hd}: {ms:.3f} ms {fl/ms/1e9:.0f} TF | cosine vs bf16 {cos:.5f} max abs diff {(y8 - y16).abs().max().item():.4f}")
+        res[f"fp8_{b}x{sq}x{sk}x{h}x{hd}"] = dict(ms=ms, tflops=fl / ms / 1e9, cos_vs_bf16=cos)
     out["attn_perf"] = res
 
 
