@@ -527,9 +527,10 @@ def secondary_workload(name, args, world, device, pk, rank):
     if uly is not None:
         out["ulysses_parity"] = ulysses_parity(name, model, dev_in, uly, device)
     eager = fn
-    if name in ("flux", "sd3") and not args.no_graph:
+    if (name in ("flux", "sd3") or (name == "qwen" and world == 1)) and not args.no_graph:
         from fastdm_b200.graph import GraphedStep
-        fn = GraphedStep(fn, dev_in)
+        fn = GraphedStep(fn, dev_in)      # (the Ulysses steps stay eager: NCCL + symmetric-memory barriers)
+        out["launch"] = "whole step replayed as one CUDA graph (fastdm_b200.graph.GraphedStep)"
     out["ms_per_step"] = ms = timed_steps(fn, dev_in, 10, 3, world, device)
     e2e, h2d, d2h = timed_e2e(fn, host, 5, world, device)
     out.update(e2e_ms=e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, step_tflops_per_s=STEP_TFLOP[name] * 1e3 / ms)
@@ -604,6 +605,7 @@ def main():
     ap.add_argument("--no-sd3", action="store_true", help="skip the secondary SD3.5 numbers at N=1")
     ap.add_argument("--no-qwen", action="store_true", help="skip the secondary Qwen-Image numbers (timed at every N)")
     ap.add_argument("--no-sparse", action="store_true", help="skip the radial-sparse Wan variant at N=1")
+    ap.add_argument("--no-fp8-attention", action="store_true", help="skip the fp8-attention Wan variant at N=1")
     ap.add_argument("--no-graph", action="store_true", help="launch the FLUX step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the reference-torch-backend-on-this-GPU leg at N=1")
@@ -659,7 +661,7 @@ def main():
     if ulysses is not None:
         # sharded == unsharded, checked on the device before anything is timed (2 blocks of the same model)
         extra["ulysses_parity"] = ulysses_parity(wl, model, dev_inputs, ulysses, device)
-    if wl in ("flux", "sd3") and not args.no_graph:
+    if (wl in ("flux", "sd3") or (wl == "qwen" and world == 1)) and not args.no_graph:
         from fastdm_b200.graph import GraphedStep
         fn = GraphedStep(fn, dev_inputs)   # 700-1300 short launches per step: replayed as one CUDA graph
 
@@ -681,6 +683,10 @@ def main():
         ulysses.stub_comm = False
         extra["a2a_exposed_ms"] = ms - ms_stub
         extra["ms_per_step_comm_stubbed"] = ms_stub
+        extra["ulysses_exchange"] = ("Q | K | V: NCCL all_to_all_single per projection group on a side stream under the next "
+                                     "group's GEMM; O: " + ("attention epilogue stores into the owners' symmetric-memory buffers "
+                                     "over NVLink (fdm_attn_fwd_scatter) + device-side barrier" if ulysses.scatter else
+                                     "NCCL all_to_all_single + unpack kernel"))
     roof = attention_roofline(wl, world if sequence_parallel else 1, device, pk)
     if rank == 0 and world == 1:
         extra["gemm"] = gemm_roofline(wl, device, pk)
@@ -702,6 +708,22 @@ def main():
                                    "dense_layers 1, all steps sparse", block_sparsity=1.0 - conv.float().mean().item(),
                                    speedup_vs_dense=ms / sms)
         del smask, m64, conv
+    if rank == 0 and secondary and world == 1 and not args.no_fp8_attention:
+        # north_star family 2 "bf16 and FP8 QK^T/PV": the same step with e4m3 q/k/v and e4m3 P in self-attention
+        # (fdm_attn_fwd with FDM_E4M3 operands; semantics csrc/attention/interface.cu:262-270)
+        ref_out = fn(dev_inputs).float()
+        for blk in model.blocks:
+            blk.fp8_attention = True
+        fp8_out = fn(dev_inputs).float()
+        fms = timed_steps(fn, dev_inputs, max(1, min(args.steps, 3)), 3, 1, device)
+        for blk in model.blocks:
+            blk.fp8_attention = False
+        cosv = torch.nn.functional.cosine_similarity(ref_out.flatten().double(), fp8_out.flatten().double(), dim=0)
+        extra["wan_fp8_attention"] = dict(ms_per_step=fms, speedup_vs_bf16_attention=ms / fms,
+                                          cos_vs_bf16_attention_step_output=float(cosv),
+                                          note="q/k/v cast to e4m3 with unit scales (one extra pass over the fused qkv buffer "
+                                               "per block, inside the timed step), P quantised to e4m3 unscaled, f32 accumulate")
+        del ref_out, fp8_out
     if secondary:
         # the other BASELINE configurations, reported next to the headline one (same timing rules). FLUX and SD3.5 are
         # single-GPU models (N = 1 only); Qwen-Image is sequence-parallel and is timed at every N.

@@ -388,6 +388,9 @@ class WanTransformerBlock:
         self.ffn = FeedForward(load_linear(sd, [f"{p}.ffn.net.0.proj"], q, dv), load_linear(sd, [f"{p}.ffn.net.2"], q, dv))
         self.scale_shift_table = sd[f"{p}.scale_shift_table"].to(dv)
         self.scale = self.hd ** -0.5
+        # optional: self-attention with e4m3 q/k/v and e4m3 P (the reference's fp8 attention semantics,
+        # csrc/attention/interface.cu:262-270: unit descales, P quantised unscaled); single-GPU path
+        self.fp8_attention = False
 
     @staticmethod
     def merge_rotary(rotary_emb, dtype):
@@ -441,6 +444,8 @@ class WanTransformerBlock:
                                                      round_steps=False)[:3])
         if ulysses is None or ulysses.P == 1:
             qkv = self.self_attention_qkv(xq, B, S, rope_table, pos0)
+            if self.fp8_attention and sparse_mask is None:
+                qkv = qkv.to(torch.float8_e4m3fn)      # one cast pass over the fused buffer (unit scales)
             attn = ops.attention(qkv[:, :, :d], qkv[:, :, d:2 * d], qkv[:, :, 2 * d:], H, hd, self.scale,
                                  sparse_mask, block_q, block_k)
         elif overlap:

@@ -424,15 +424,19 @@ __global__ void __launch_bounds__(256) rmsnorm_long_kernel(const T* __restrict__
   const int64_t row = blockIdx.x;
   const int nvec = cols >> 3;
   const T* src = in + row * in_stride;
-  float f[VPT][8];
+  // the row stays in registers as packed 16-byte vectors (4 registers per vector, not 8 floats): occupancy, and for
+  // bf16 the second pass works on the packed form directly
+  U128 raw[VPT];
   float ss = 0.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
-      unpack8<T>(ldg128_stream(src + (int64_t)v * 8), f[i]);
+      raw[i] = ldg128_stream(src + (int64_t)v * 8);
+      float f[8];
+      unpack8<T>(raw[i], f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ss += f[i][j] * f[i][j];
+      for (int j = 0; j < 8; ++j) ss = fmaf(f[j], f[j], ss);
     }
   }
   ss = block_sum(ss, red);
@@ -442,15 +446,25 @@ __global__ void __launch_bounds__(256) rmsnorm_long_kernel(const T* __restrict__
   for (int i = 0; i < VPT; ++i) {
     const int v = threadIdx.x + i * blockDim.x;
     if (v < nvec) {
+      float f[8];
+      unpack8<T>(raw[i], f);
+      if constexpr (Elem<T>::kId == FDM_BF16) {
+        if (w != nullptr) {   // T(T(x * rs) * w): one fp32 multiply, one packed bf16 multiply per pair (bit-identical)
+          uint32_t o[4];
+          norm_scale8_bf16(f, rs, ldg128(w + (int64_t)v * 8), o);
+          stg128(dst + (int64_t)v * 8, U128{o[0], o[1], o[2], o[3]});
+          continue;
+        }
+      }
       float o[8];
       if (w != nullptr) {
         float wv[8];
         unpack8<T>(ldg128(w + (int64_t)v * 8), wv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = round_to<T>(f[i][j] * rs) * wv[j];
+        for (int j = 0; j < 8; ++j) o[j] = round_to<T>(f[j] * rs) * wv[j];
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = f[i][j] * rs;
+        for (int j = 0; j < 8; ++j) o[j] = f[j] * rs;
       }
       stg128(dst + (int64_t)v * 8, pack8<T>(o));
     }
@@ -1272,18 +1286,23 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
           c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
         }
         float f[8];
+        if constexpr (!ROUND_STEPS) {
+          // fp32 chain (Wan): T(n * A + C) with the product and the sum rounded separately, two lanes at a time
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float t = n[j];
-          if (ROUND_STEPS) {
-            t = round_to<T>(t);
+          for (int q = 0; q < 4; ++q) {
+            uint64_t t2 = pk2(n[2 * q], n[2 * q + 1]);
+            if (Ar) t2 = mul2f(t2, pk2(a[2 * q], a[2 * q + 1]));
+            if (Cr) t2 = add2f(t2, pk2(c[2 * q], c[2 * q + 1]));
+            upk2(t2, f[2 * q], f[2 * q + 1]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = round_to<T>(n[j]);
             if (Ar) t = round_to<T>(__fmul_rn(t, a[j]));
             if (Cr) t = __fadd_rn(t, c[j]);
-          } else {
-            if (Ar) t = __fmul_rn(t, a[j]);
-            if (Cr) t = __fadd_rn(t, c[j]);
+            f[j] = t;
           }
-          f[j] = t;
         }
         raw[i] = pack8<T>(f);
         const uint32_t y[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};

@@ -378,6 +378,7 @@ class QwenImageTransformer2DModelCore:
     def __init__(self, num_layers=60, attention_head_dim=128, num_attention_heads=24, in_channels=64, out_channels=64,
                  joint_attention_dim=3584, patch_size=2, axes_dims_rope=(16, 56, 56), quant_dtype=torch.int8,
                  device="cuda", seed=0, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        self._rope_cache = {}
         self.heads, self.hd = num_attention_heads, attention_head_dim
         self.inner_dim = d = self.heads * self.hd
         self.axes_dims_rope = axes_dims_rope
@@ -425,7 +426,10 @@ class QwenImageTransformer2DModelCore:
         temb = self.timestep_embedder.forward(
             get_timestep_embedding(timestep.to(dt), 256, flip_sin_to_cos=True, downscale_freq_shift=0, scale=1000).to(dt))
         T = enc.shape[1]
-        rope = qwen_rope_table(*img_shape, T, self.axes_dims_rope, dtype=dt, device=x.device)
+        key = (tuple(img_shape), T, dt, str(x.device))
+        rope = self._rope_cache.get(key)      # the table only depends on the shapes: built once (on the host), reused
+        if rope is None:
+            rope = self._rope_cache[key] = qwen_rope_table(*img_shape, T, self.axes_dims_rope, dtype=dt, device=x.device)
         rope_pos = None
         if ulysses is not None and ulysses.P > 1:
             x = ulysses.shard_tokens(x, dim=1)
