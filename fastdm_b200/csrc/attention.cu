@@ -42,6 +42,15 @@ constexpr int kQTile = 128;   // rows per Q tile (UMMA M)
 constexpr int kKvTile = 128;  // keys per KV tile (UMMA N of QK^T, K extent of PV)
 constexpr int kMaxKvTiles = 8192;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units
+// The MMA issuer: one elected thread runs the whole issue loop (1) or the warp runs it converged and elects a lane per
+// instruction (0). Inside `if (elect_one())` ptxas keeps descriptors, addresses and predicates on the uniform datapath:
+// ~3 uniform instructions per tcgen05.mma instead of ~13 (ELECT, 2 VOTEU, 4 R2UR, UMOVs), which matters because the
+// issuing warp shares its scheduler with two softmax warps (tools/softmax_lab.cu: +15-20 cycles per MMA under that load
+// with the per-instruction election, +2-3 with one thread).
+#ifndef FDM_ATTN_ONE_ISSUER
+#define FDM_ATTN_ONE_ISSUER 1
+#endif
+constexpr bool kOneIssuer = FDM_ATTN_ONE_ISSUER != 0;
 
 template <int HD, int ES, bool PS, int CG>
 struct AttnSmem {
@@ -361,8 +370,9 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
     // but drops to ~87 cycles when two threads' MMAs interleave (tools/cg2_rate.cu). A tcgen05.mma blocks
     // its thread once ~4 are queued (tools/mma_queue.cu), so whatever the thread does between two groups
     // of MMAs has to fit under ~256 cycles of queued work or the pipe drains.
-    // The whole warp runs the loop converged; the MMAs and commits themselves go out from one elected lane.
-    if (rank == 0) {
+    // kOneIssuer: one elected thread runs the loop; else the whole warp runs it converged and the MMAs and commits
+    // themselves go out from one elected lane.
+    if (rank == 0 && (!kOneIssuer || elect_one())) {
       // per-Q-tile operands as scalars (x is a run-time value for the two PS issuers)
       auto tS_of = [&](int x) { return tmem_base + (uint32_t)x * 128u; };
       auto tO_of = [&](int x) { return tmem_base + 256u + (uint32_t)x * 128u; };
@@ -370,8 +380,13 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
       auto q_desc_of = [&](int x) { return make_desc_kmajor_sw128(base + S::kQOff + (uint32_t)x * S::kTileBytes); };
       auto p_desc_of = [&](int x) { return make_desc_kmajor_sw128(base + S::kPOff + (uint32_t)x * S::kPBytes); };
       auto commit = [&](uint32_t bar) {
-        if (CG == 2) tc_commit_cg2_elect(bar, 0b11);  // the same barrier in both CTAs of the pair
-        else tc_commit_elect(bar);
+        if (kOneIssuer) {
+          if (CG == 2) tc_commit_cg2(bar, 0b11);  // the same barrier in both CTAs of the pair
+          else tc_commit(bar);
+        } else {
+          if (CG == 2) tc_commit_cg2_elect(bar, 0b11);
+          else tc_commit_elect(bar);
+        }
       };
       // `probe` runs after the 7th MMA of a group -- with the queue full, i.e. for free (one late probe measured
       // no worse than two earlier ones and succeeds more often)
@@ -384,7 +399,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           const uint64_t off = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
           // a CTA of a pair holds kKvTile / 2 keys per head-dim panel
           const uint64_t koff = (uint64_t)(((ks / 4) * (kKvTile / CG * 128) + (ks % 4) * 32) >> 4);
-          umma_ss<kKind, CG, true>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
+          umma_ss<kKind, CG, !kOneIssuer>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
           if (ks == 6) probe();
         }
       };
@@ -402,9 +417,9 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
           if (PS) {
             const uint64_t poff = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
-            umma_ss<kKind, CG, true>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
+            umma_ss<kKind, CG, !kOneIssuer>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
           } else {
-            umma_ts<kKind, true>(tO, tP + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
+            umma_ts<kKind, !kOneIssuer>(tO, tP + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
           }
           if (ks == (kKvTile / kKeysPerPV) * 7 / 8 - 1) probe();
         }
@@ -414,7 +429,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
         mbar_wait(kv_full(u % S::kStages), (u / S::kStages) & 1u);
         tc_fence_after();
       };
-      const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+      const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (kOneIssuer || lane == 0);
 
       int j = next_active(0);
       if (j < p.n_kv_tiles) {
