@@ -51,6 +51,11 @@ constexpr float kRescaleThreshold = 8.0f;  // log2 units
 #define FDM_ATTN_ONE_ISSUER 1
 #endif
 constexpr bool kOneIssuer = FDM_ATTN_ONE_ISSUER != 0;
+// dense calls whose P does not alias S: MMA groups are issued in order of readiness instead of round-robin (see the issuer)
+#ifndef FDM_ATTN_DYN
+#define FDM_ATTN_DYN 0
+#endif
+constexpr bool kDynIssue = FDM_ATTN_DYN != 0;
 
 template <int HD, int ES, bool PS, int CG>
 struct AttnSmem {
@@ -78,7 +83,7 @@ struct AttnParams {
   int n_kv_tiles;
   int mask_bq, mask_bk, nbq, nbk;
   float scale_log2;
-  int reserved;      // (kept: the layout of this struct is part of the measured build, see attention_persistent.cu)
+  int stagger;       // cycles by which Q tile B's first QK is held back (readiness-driven issue order)
   long long* trace;  // debug: per-event clock64 stamps of CTA (0,0,0), or nullptr
 };
 
@@ -436,7 +441,70 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
         mbar_wait(q_full, 0);
         tc_fence_after();
         wait_full(0);
-        if (DEC) {
+        if (DEC && !MASKED && kDynIssue) {
+          // Readiness-driven issue order (dense calls): the four groups of a tile -- QK_A(t+1), QK_B(t+1), PV_A(t), PV_B(t) --
+          // have independent conditions (S_X free + K landed / P_X written + V landed), and with a fixed round-robin
+          // order a group whose condition was met long ago waits behind one that is still blocked: QK_X(t+1) went out
+          // ~1800 cycles after S_X became free, the softmax warps then waited ~500 cycles per tile for S and ~300 for
+          // their P buffer (in-kernel timeline). Here the thread polls all four conditions and issues whichever group
+          // is ready; the softmax of tile t then always finds S(t+1) and a free P buffer. Issue itself is cheap
+          // (one thread, uniform datapath), so the polling does not hold the tensor pipe back.
+          // Ring items (dense): K(0) | K(t+1), V(t) | ... -> item of K(t) = 2t - 1 (t >= 1), of V(t) = 2t + 2, last V = 2n - 1.
+          const uint32_t n = (uint32_t)p.n_kv_tiles;
+          auto item_k = [&](uint32_t t) { return t == 0 ? 0u : 2u * t - 1u; };
+          auto item_v = [&](uint32_t t) { return t + 1 < n ? 2u * t + 2u : 2u * n - 1u; };
+          auto item_stage = [&](uint32_t it) { return it % (uint32_t)S::kStages; };
+          auto item_par = [&](uint32_t it) { return (it / (uint32_t)S::kStages) & 1u; };
+          auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
+          uint32_t qk_t[2] = {0u, 0u}, pv_t[2] = {0u, 0u};
+          // Q tile B starts p.stagger cycles after Q tile A: two softmax warps that share a scheduler should not be in their
+          // exponential phases at the same time (MUFU is the one unit both saturate), and nothing else pulls them apart
+          const long long t_b0 = clock64() + p.stagger;
+          while (pv_t[0] < n || pv_t[1] < n) {
+            // one round: the four conditions are probed back to back (independent ~40-cycle barrier reads), then every
+            // group found ready is issued. A condition that was true stays true, so a stale positive is still valid.
+            bool rq[2], rp[2];
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              const uint32_t tq = qk_t[x], tp = pv_t[x];
+              const bool sf = mbar_test_wait(s_free(x), (tq - 1u) & 1u);
+              const bool pr = mbar_test_wait(p_ready(x), tp & 1u);
+              rq[x] = tq < n && (tq == 0 ? (x == 0 || clock64() >= t_b0) : sf);
+              rp[x] = tp < tq && pr;
+            }
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+              // ---- QK_X(t): S_X(t-1) is in the softmax warps' registers, K(t) landed ----
+              if (rq[x]) {
+                const uint32_t tq = qk_t[x];
+                const uint32_t it = item_k(tq);
+                if (mbar_test_wait(kv_full(item_stage(it)), item_par(it))) {
+                  tc_fence_after();
+                  trace_ev(p, tr, 2 + x, 0, tq);
+                  issue_qk(x, stage_smem(item_stage(it)), no_probe);
+                  commit(s_full(x));
+                  if (qk_t[x ^ 1] > tq) commit(kv_empty(item_stage(it)));  // the other Q tile used K(t) already: slot free
+                  trace_ev(p, tr, 2 + x, 1, tq);
+                  qk_t[x] = tq + 1;
+                }
+              }
+              // ---- PV_X(t): P_X(t) written, V(t) landed ----
+              if (rp[x]) {
+                const uint32_t tp = pv_t[x];
+                const uint32_t it = item_v(tp);
+                if (mbar_test_wait(kv_full(item_stage(it)), item_par(it))) {
+                  tc_fence_after();
+                  trace_ev(p, tr, 2 + x, 2, tp);
+                  issue_pv(x, stage_smem(item_stage(it)), tp != 0, no_probe);
+                  commit(o_done(x));
+                  if (pv_t[x ^ 1] > tp) commit(kv_empty(item_stage(it)));
+                  trace_ev(p, tr, 2 + x, 3, tp);
+                  pv_t[x] = tp + 1;
+                }
+              }
+            }
+          }
+        } else if (DEC) {
           // P travels through shared memory (or spare TMEM columns), so S_X is free again as soon as the softmax warps hold it in
           // registers: QK_X(t+1) is issued ahead of PV_X(t) and the only per-tile dependency chain left is
           // the softmax itself. Per active tile t the groups go QK_A(t+1), PV_A(t), QK_B(t+1), PV_B(t); ring
@@ -680,7 +748,11 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
       apply_mask(s1, 1);
       apply_mask(s2, 2);
       apply_mask(s3, 3);
+#ifdef FDM_ATTN_CHEAT_NOMAX
+      const float mx = t == 0 ? fmaxf(fmax3(max32(s0), max32(s1), max32(s2)), max32(s3)) + 6.f : -INFINITY;   // (upper-bound experiment only)
+#else
       const float mx = fmaxf(fmax3(max32(s0), max32(s1), max32(s2)), max32(s3));
+#endif
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool need = m_new > m_run + kRescaleThreshold;  // first finite max always triggers
       if (__any_sync(0xffffffffu, need)) {
@@ -952,6 +1024,10 @@ static int attn_env(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
+static int attn_env_stagger() {
+  static const int v = attn_env("FDM_ATTN_STAGGER", 1200);
+  return v;
+}
 static bool attn_pair_setting() {
   static int v = attn_env("FDM_ATTN_CG", 2);
   return v == 2;
@@ -975,9 +1051,12 @@ static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
 
 // how many of every 32 exponentials run on the FMA pipe instead of MUFU (tuning knob; the default is
 // the measured optimum, FDM_ATTN_EMU overrides it for experiments)
-static int attn_emu_setting(int hd) {
+static int attn_emu_setting(int hd, bool fp8) {
   static const int v = attn_env("FDM_ATTN_EMU", -1);
   if (v >= 0) return v;
+  // fp8 operands: the MMAs take half the time, so the softmax is further from hiding behind them and more of its
+  // exponentials pay off on the FMA pipe (8704^2 x 24: 1134 -> 1561 TFLOP/s, 80640^2 x 4: 1565 -> 1806 with 12 instead of 4)
+  if (fp8) return 12;
   return hd == 128 ? 4 : 12;
 }
 
@@ -990,7 +1069,7 @@ static bool attn_late_store() {
 template <int HD, int DT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                        const AttnParams& p, cudaStream_t st, const ScatterParams* sp = nullptr) {
-  const int emu = attn_emu_setting(HD);
+  const int emu = attn_emu_setting(HD, DT == kDtE4M3);
   if (attn_late_store()) {
     if (emu <= 0) return launch_attn_e<HD, DT, 64 + 0>(tq, tk, tv, p, st, sp);
     if (emu <= 4) return launch_attn_e<HD, DT, 64 + 4>(tq, tk, tv, p, st, sp);
@@ -1094,7 +1173,7 @@ static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, v
     p.nbk = (int)((Sk + mask_bk - 1) / mask_bk);
   }
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.reserved = 0;
+  p.stagger = attn_env_stagger();
   p.trace = g_attn_trace;
   ScatterParams sc;
   sc.rows_per_peer = 0;
