@@ -56,6 +56,22 @@ constexpr bool kOneIssuer = FDM_ATTN_ONE_ISSUER != 0;
 #define FDM_ATTN_DYN 0
 #endif
 constexpr bool kDynIssue = FDM_ATTN_DYN != 0;
+// dense calls: each P arrival releases the other Q tile's next QK before its own PV (see the issuer)
+#ifndef FDM_ATTN_QK_FIRST
+#define FDM_ATTN_QK_FIRST 0
+#endif
+constexpr bool kQkFirst = FDM_ATTN_QK_FIRST != 0;
+// issue pacing window in batches of 2 MMAs (0 = off; see the issuer)
+#ifndef FDM_ATTN_PACE
+#define FDM_ATTN_PACE 0
+#endif
+constexpr int kPace = FDM_ATTN_PACE;
+// dense calls whose P does not alias S: warps 9, 10, 11 take turns at issuing the MMA groups (see the issuer)
+#ifndef FDM_ATTN_ROTATE
+#define FDM_ATTN_ROTATE 1
+#endif
+constexpr bool kRotate = FDM_ATTN_ROTATE != 0 && kOneIssuer && kPace == 0;
+constexpr int kIssuers = 3;
 
 template <int HD, int ES, bool PS, int CG>
 struct AttnSmem {
@@ -68,7 +84,7 @@ struct AttnSmem {
   static constexpr int kPOff = 2 * kTileBytes;
   static constexpr int kKvOff = kPOff + 2 * kPBytes;
   static constexpr int kBarOff = kKvOff + kStages * kKvBytes;
-  static constexpr int kNumBars = 1 + 2 * kStages + 8;
+  static constexpr int kNumBars = 1 + 2 * kStages + 8 + 4;   // q_full, ring full/empty, 8 pipeline barriers, 4 issue-pacing barriers
   static constexpr int kFlagsOff = kBarOff + kNumBars * 8 + 16;
   static constexpr int kTotal = kFlagsOff + kMaxKvTiles / 8 + 1024;  // one flag bit per KV tile; 1 KB alignment slack
   static_assert(kTotal <= 232448, "attention: shared-memory layout exceeds 227 KB");
@@ -219,6 +235,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
   auto p_ready = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 2 + x); };
   auto o_done = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 4 + x); };
   auto s_free = [&](int x) { return bar_base + 8u * (1 + 2 * S::kStages + 6 + x); };
+  auto pace_bar = [&](uint32_t b) { return bar_base + 8u * (1 + 2 * S::kStages + 8 + (b & 3u)); };
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + S::kBarOff + S::kNumBars * 8);
   uint8_t* flags = smem + S::kFlagsOff;
 
@@ -254,6 +271,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
       mbar_init(kv_full(s), 1);
       mbar_init(kv_empty(s), 1);
     }
+    for (uint32_t i = 0; i < 4; ++i) mbar_init(pace_bar(i), 1);
     for (int x = 0; x < 2; ++x) {
       mbar_init(s_full(x), 1);
       mbar_init(o_done(x), 1);
@@ -369,7 +387,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
       }
     }
     __syncwarp();
-  } else if (warp == 9) {
+  } else if (warp == 9 || (kRotate && DEC && !MASKED && !TRACE)) {
     // ===================== MMA issuer (the leader CTA's, for a pair) =====================
     // One thread issues everything: the tensor pipe runs one thread's MMAs back to back at 64 cycles each,
     // but drops to ~87 cycles when two threads' MMAs interleave (tools/cg2_rate.cu). A tcgen05.mma blocks
@@ -393,6 +411,28 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           else tc_commit_elect(bar);
         }
       };
+      // Issue pacing: a tcgen05.mma whose thread already has ~4 queued blocks at issue, and while it is blocked the softmax
+      // warps on the same scheduler make almost no progress (per-warp arrival stamps: the two warps that share warp 9's
+      // scheduler arrive 400-1600 cycles after the other six, and every P hand-over waits for the last warp). So the
+      // thread never lets more than kPace batches of 2 MMAs be outstanding: each batch commits to one of four pacing
+      // barriers and batch b first waits (mbarrier.try_wait: the thread is suspended, not blocked at issue) for batch
+      // b - kPace to have completed.
+      uint32_t pace_b = 0;
+      auto pace_before = [&]() {
+        if constexpr (kPace > 0 && kOneIssuer) {
+          if (pace_b >= (uint32_t)kPace) {
+            const uint32_t w = pace_b - (uint32_t)kPace;
+            mbar_wait(pace_bar(w), (w >> 2) & 1u);
+          }
+        }
+      };
+      auto pace_after = [&]() {
+        if constexpr (kPace > 0 && kOneIssuer) {
+          if (CG == 2) tc_commit_cg2(pace_bar(pace_b), 0b01);  // (this CTA's barrier only: the issuing thread is the one that waits)
+          else tc_commit(pace_bar(pace_b));
+          ++pace_b;
+        }
+      };
       // `probe` runs after the 7th MMA of a group -- with the queue full, i.e. for free (one late probe measured
       // no worse than two earlier ones and succeeds more often)
       auto issue_qk = [&](int x, uint32_t k_smem, auto&& probe) {
@@ -404,7 +444,9 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           const uint64_t off = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
           // a CTA of a pair holds kKvTile / 2 keys per head-dim panel
           const uint64_t koff = (uint64_t)(((ks / 4) * (kKvTile / CG * 128) + (ks % 4) * 32) >> 4);
+          if ((ks & 1) == 0) pace_before();
           umma_ss<kKind, CG, !kOneIssuer>(tS, q_desc + off, k_desc + koff, kIdescQK, ks != 0);
+          if ((ks & 1) == 1) pace_after();
           if (ks == 6) probe();
         }
       };
@@ -420,12 +462,14 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           // K-major rows in shared memory (PS) or 8 TMEM columns
           const uint64_t voff = (uint64_t)((ks * kKeysPerPV * 128) >> 4);
           const uint32_t acc = (accumulate || ks != 0) ? 1u : 0u;
+          if ((ks & 1) == 0) pace_before();
           if (PS) {
             const uint64_t poff = (uint64_t)(((ks / 4) * (kQTile * 128) + (ks % 4) * 32) >> 4);
             umma_ss<kKind, CG, !kOneIssuer>(tO, p_desc + poff, v_desc + voff, kIdescPV, acc);
           } else {
             umma_ts<kKind, !kOneIssuer>(tO, tP + (uint32_t)ks * 8u, v_desc + voff, kIdescPV, acc);
           }
+          if ((ks & 1) == 1) pace_after();
           if (ks == (kKvTile / kKeysPerPV) * 7 / 8 - 1) probe();
         }
       };
@@ -441,7 +485,167 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
         mbar_wait(q_full, 0);
         tc_fence_after();
         wait_full(0);
-        if (DEC && !MASKED && kDynIssue) {
+        if (DEC && !MASKED && !TRACE && kRotate) {
+          // Rotating issuers (dense calls). A tcgen05.mma whose thread already has ~4 queued blocks at issue, and while it is
+          // blocked the two softmax warps on the same scheduler make almost no progress (per-warp arrival stamps with one
+          // issuer on warp 9: warps 1 and 5 hand their P rows over 400-1600 cycles after the other six, and every PV waits
+          // for the last row). Pacing the issue through commit barriers starves the pipe (-10 %), so the stall is spread
+          // instead: warps 9, 10 and 11 -- one per scheduler next to the TMA warp's -- run the same group sequence
+          //     QK_A(0) QK_B(0) | QK_A(t+1) PV_A(t) QK_B(t+1) PV_B(t) | ...
+          // and group g is issued by issuer g mod 3, after a token from the issuer of group g - 1 (issue order = pipe order;
+          // a commit only tracks its own thread's MMAs, which is enough because the pipe completes them in issue order).
+          // Every issuer waits itself for the barriers of the groups it issues.
+          const uint32_t n = (uint32_t)p.n_kv_tiles;
+          const uint32_t me = (uint32_t)(warp - 9);
+          auto item_k = [&](uint32_t t) { return t == 0 ? 0u : 2u * t - 1u; };
+          auto item_v = [&](uint32_t t) { return t + 1 < n ? 2u * t + 2u : 2u * n - 1u; };
+          auto item_stage = [&](uint32_t it) { return it % (uint32_t)S::kStages; };
+          auto item_par = [&](uint32_t it) { return (it / (uint32_t)S::kStages) & 1u; };
+          auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
+          uint32_t g = 0, mine = 0;   // group counter, number of groups this issuer has taken
+          auto my_turn = [&]() {      // is group g mine? if so, wait for the token of group g - 1
+            const bool yes = g % (uint32_t)kIssuers == me;
+            if (yes && g > 0) mbar_wait(pace_bar(me), mine & 1u);
+            return yes;
+          };
+          auto pass_on = [&]() {      // group g is in the queue: the next issuer may go
+            mbar_arrive(pace_bar((me + 1u) % (uint32_t)kIssuers));
+            ++mine;
+          };
+          // group 0 goes out without a token, so issuer 0's token count is one behind the others'
+          if (my_turn()) {
+            issue_qk(0, stage_smem(0), no_probe);
+            commit(s_full(0));
+            pass_on();
+            if (me == 0) --mine;
+          }
+          ++g;
+          if (my_turn()) {
+            issue_qk(1, stage_smem(0), no_probe);
+            commit(s_full(1));
+            commit(kv_empty(0));
+            pass_on();
+          }
+          ++g;
+          for (uint32_t t = 0; t < n; ++t) {
+            const uint32_t ph = t & 1u;
+            const uint32_t iv = item_v(t), ik = item_k(t + 1);
+            const bool has_next = t + 1 < n;
+            if (has_next) {
+              if (my_turn()) {   // QK_A(t+1)
+                mbar_wait(kv_full(item_stage(ik)), item_par(ik));
+                mbar_wait(s_free(0), ph);
+                tc_fence_after();
+                issue_qk(0, stage_smem(item_stage(ik)), no_probe);
+                commit(s_full(0));
+                pass_on();
+              }
+              ++g;
+            }
+            if (my_turn()) {     // PV_A(t)
+              mbar_wait(kv_full(item_stage(iv)), item_par(iv));
+              mbar_wait(p_ready(0), ph);
+              tc_fence_after();
+              issue_pv(0, stage_smem(item_stage(iv)), t != 0, no_probe);
+              commit(o_done(0));
+              pass_on();
+            }
+            ++g;
+            if (has_next) {
+              if (my_turn()) {   // QK_B(t+1)
+                mbar_wait(kv_full(item_stage(ik)), item_par(ik));
+                mbar_wait(s_free(1), ph);
+                tc_fence_after();
+                issue_qk(1, stage_smem(item_stage(ik)), no_probe);
+                commit(s_full(1));
+                commit(kv_empty(item_stage(ik)));
+                pass_on();
+              }
+              ++g;
+            }
+            if (my_turn()) {     // PV_B(t)
+              mbar_wait(kv_full(item_stage(iv)), item_par(iv));
+              mbar_wait(p_ready(1), ph);
+              tc_fence_after();
+              issue_pv(1, stage_smem(item_stage(iv)), t != 0, no_probe);
+              commit(o_done(1));
+              commit(kv_empty(item_stage(iv)));
+              pass_on();
+            }
+            ++g;
+          }
+        } else if (DEC && !MASKED && kQkFirst) {
+          // Dense calls, QK-first order. What the softmax warps of Q tile X wait for at the end of tile t is S_X(t+1); what
+          // they need ~1800 cycles later is their P buffer back (PV_X(t) done). With the round-robin order below, the thread
+          // that has just seen P_B(t-1) issues PV_B(t-1) and only then QK_A(t+1): S_A(t+1) queues behind 8 MMAs it does not
+          // depend on and arrives ~300-500 cycles after tile A's softmax wanted it (in-kernel timeline: that wait, per tile,
+          // on both Q tiles). Here each P arrival releases the OTHER tile's next QK first and the PV second:
+          //     wait P_A(t) | QK_B(t+1) | PV_A(t) | wait P_B(t) | QK_A(t+2) | PV_B(t)
+          // The blocking waits keep the two softmax warpgroups half a tile apart (B's next S is only issued once A has
+          // finished a tile and vice versa), which matters: in phase, both hit the MUFU unit at once and a tile's
+          // exponentials take 1950 cycles instead of 1300 (measured with the readiness-driven order).
+          // Ring items as above: K(0) | K(t+1), V(t) | ...; K(t+2) is first used one iteration before QK_B(t+2) frees it.
+          const uint32_t n = (uint32_t)p.n_kv_tiles;
+          auto item_k = [&](uint32_t t) { return t == 0 ? 0u : 2u * t - 1u; };
+          auto item_v = [&](uint32_t t) { return t + 1 < n ? 2u * t + 2u : 2u * n - 1u; };
+          auto item_stage = [&](uint32_t it) { return it % (uint32_t)S::kStages; };
+          auto item_par = [&](uint32_t it) { return (it / (uint32_t)S::kStages) & 1u; };
+          auto stage_smem = [&](uint32_t st) { return base + S::kKvOff + st * S::kKvBytes; };
+          issue_qk(0, stage_smem(0), no_probe);
+          commit(s_full(0));
+          issue_qk(1, stage_smem(0), no_probe);
+          commit(s_full(1));
+          commit(kv_empty(0));
+          if (n > 1) {
+            const uint32_t ik = item_k(1);
+            mbar_wait(kv_full(item_stage(ik)), item_par(ik));
+            mbar_wait(s_free(0), 0u);
+            tc_fence_after();
+            issue_qk(0, stage_smem(item_stage(ik)), no_probe);
+            commit(s_full(0));
+          }
+          for (uint32_t t = 0; t < n; ++t) {
+            const uint32_t ph = t & 1u;
+            const uint32_t iv = item_v(t);
+            // ---- P_A(t) written: QK_B(t+1), then PV_A(t) ----
+            trace_ev(p, tr, 2, 4, t);
+            mbar_wait(p_ready(0), ph);
+            trace_ev(p, tr, 2, 0, t);
+            if (t + 1 < n) {
+              const uint32_t ik = item_k(t + 1);
+              mbar_wait(s_free(1), ph);   // S_B(t) is in registers (K(t+1) landed before QK_A(t+1) went out)
+              tc_fence_after();
+              issue_qk(1, stage_smem(item_stage(ik)), no_probe);
+              commit(s_full(1));
+              commit(kv_empty(item_stage(ik)));
+            }
+            trace_ev(p, tr, 2, 1, t);
+            mbar_wait(kv_full(item_stage(iv)), item_par(iv));
+            tc_fence_after();
+            trace_ev(p, tr, 2, 2, t);
+            issue_pv(0, stage_smem(item_stage(iv)), t != 0, no_probe);
+            commit(o_done(0));
+            trace_ev(p, tr, 2, 3, t);
+            // ---- P_B(t) written: QK_A(t+2), then PV_B(t) ----
+            mbar_wait(p_ready(1), ph);
+            trace_ev(p, tr, 3, 0, t);
+            if (t + 2 < n) {
+              const uint32_t ik = item_k(t + 2);
+              mbar_wait(kv_full(item_stage(ik)), item_par(ik));
+              mbar_wait(s_free(0), ph ^ 1u);   // S_A(t+1) is in registers
+              tc_fence_after();
+              issue_qk(0, stage_smem(item_stage(ik)), no_probe);
+              commit(s_full(0));
+            }
+            trace_ev(p, tr, 3, 1, t);
+            tc_fence_after();
+            trace_ev(p, tr, 3, 2, t);
+            issue_pv(1, stage_smem(item_stage(iv)), t != 0, no_probe);
+            commit(o_done(1));
+            commit(kv_empty(item_stage(iv)));
+            trace_ev(p, tr, 3, 3, t);
+          }
+        } else if (DEC && !MASKED && kDynIssue) {
           // Readiness-driven issue order (dense calls): the four groups of a tile -- QK_A(t+1), QK_B(t+1), PV_A(t), PV_B(t) --
           // have independent conditions (S_X free + K landed / P_X written + V landed), and with a fixed round-robin
           // order a group whose condition was met long ago waits behind one that is still blocked: QK_X(t+1) went out
@@ -672,10 +876,12 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
     float l_run = 0.f;
     uint32_t t = 0;
     for (int j = next_active(0); j < p.n_kv_tiles; j = next_active(j + 1)) {
-      const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
-      trace_ev(p, tr, x, 0, t);
+      // (TRACE: roles 0/1 = this CTA's warp 0 of Q tile A/B for CTA 0; roles 4/5 = the same warps of CTA 1, the peer of a pair)
+      const bool tr = TRACE && p.trace != nullptr && blockIdx.x <= 1 && blockIdx.y == 0 && blockIdx.z == 0 && (warp & 3) == 0 && lane == 0;
+      const int xr = x + 4 * (int)blockIdx.x;
+      trace_ev(p, tr, xr, 0, t);
       mbar_wait(s_full(x), t & 1u);
-      trace_ev(p, tr, x, 1, t);
+      trace_ev(p, tr, xr, 1, t);
       tc_fence_after();
       // PS: has PV_X(t-1) finished reading the P tile? Probed here, needed only at the first store of P
       bool p_free = !DEC || t == 0;
@@ -743,7 +949,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           mbar_arrive(s_free(x));
         }
       }
-      trace_ev(p, tr, x, 2, t);
+      trace_ev(p, tr, xr, 2, t);
       apply_mask(s0, 0);
       apply_mask(s1, 1);
       apply_mask(s2, 2);
@@ -776,7 +982,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
           }
         }
       }
-      trace_ev(p, tr, x, 3, t);
+      trace_ev(p, tr, xr, 3, t);
       // the P tile (shared memory / spare TMEM columns) is read by PV_X(t-1) until o_done(x) completes its phase.
       // LS: all exponentials of the tile are computed and packed into registers first (64 registers replace the 128 of
       // S as they are consumed) and the wait comes just before the burst of stores -- PV_X(t-1) has ~the whole softmax
@@ -840,7 +1046,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
         compute(s1, pk1);
         compute(s2, pk2);
         compute(s3, pk3);
-        trace_ev(p, tr, x, 7, t);
+        trace_ev(p, tr, xr, 7, t);
         if (DEC && !p_free) mbar_wait(o_done(x), (t - 1) & 1u);
         store(pk0, 0);
         store(pk1, 1);
@@ -866,7 +1072,7 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
         l_run += (m_run == -INFINITY) ? 0.f : (a0 + a1) + (b0 + b1);
       }
       }  // !dead
-      trace_ev(p, tr, x, 4, t);
+      trace_ev(p, tr, xr, 4, t);
       if (PS) fence_proxy_async_smem();  // generic-proxy stores of P -> visible to the tensor core's reads
       if (!PS || tmem_dirty) tmem_st_wait();  // P in TMEM, or O rescaled through TMEM
       tc_fence_before();
@@ -876,9 +1082,11 @@ __device__ __forceinline__ void attn_fwd_body(const CUtensorMap& tmap_q, const C
       } else {
         mbar_arrive(p_ready(x));
       }
-      trace_ev(p, tr, x, 5, t);
-      if (TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < kTraceTiles)
-        atomicMax((unsigned long long*)&p.trace[(x * 8 + 6) * kTraceTiles + t], (unsigned long long)clock64());
+      trace_ev(p, tr, xr, 5, t);
+      // (role 6: arrival time of each of the leader CTA's eight softmax warps, event = warp)
+      trace_ev(p, TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0, 6, warp, t);
+      if (TRACE && p.trace != nullptr && blockIdx.x <= 1 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && t < kTraceTiles)
+        atomicMax((unsigned long long*)&p.trace[(xr * 8 + 6) * kTraceTiles + t], (unsigned long long)clock64());
       ++t;
     }
 
@@ -1098,7 +1306,7 @@ using namespace fdm;
 
 static long long* g_attn_trace = nullptr;
 extern "C" int fdm_debug_set_attn_trace(void* device_buffer) {
-  g_attn_trace = (long long*)device_buffer;  // 4 roles x 8 events x 64 tiles x int64, or NULL to disable
+  g_attn_trace = (long long*)device_buffer;  // 7 roles x 8 events x 64 tiles x int64, or NULL to disable
   return FDM_OK;
 }
 

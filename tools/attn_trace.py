@@ -11,12 +11,12 @@ b, s, h, hd = 1, 8704, 24, 128
 q, k, v = (torch.randn(b, s, h * hd, device="cuda", dtype=torch.bfloat16) for _ in range(3))
 for _ in range(2):
     ops.scaled_dot_product_attention(q, k, v, h, h, hd)
-buf = torch.zeros(4 * 8 * 64, dtype=torch.int64, device="cuda")
+buf = torch.zeros(7 * 8 * 64, dtype=torch.int64, device="cuda")
 lib.fdm_debug_set_attn_trace(buf.data_ptr())
 ops.scaled_dot_product_attention(q, k, v, h, h, hd)
 torch.cuda.synchronize()
 lib.fdm_debug_set_attn_trace(None)
-tr = buf.cpu().view(4, 8, 64)
+tr = buf.cpu().view(7, 8, 64)
 pair = os.environ.get("FDM_ATTN_CG", "2") == "2"
 t0 = int(tr[0, 0, 0])
 for t in range(8, 20):
@@ -37,6 +37,12 @@ for t in range(8, 20):
         m = [int(tr[2, e, t]) - t0 for e in range(6)]
         line += f" | MMA Vrdy {m[0]:6d} P_A {m[1]:6d} pv_issued +{m[4]-m[1]:4d} qk_issued +{m[2]-m[1]:4d} P_B {m[3]:6d}"
     print(line)
+    # last arrival over the four warps of each warpgroup (event 6), leader CTA and peer CTA of the pair
+    print("        | P arrival per warp (leader CTA): A " + " ".join(f"{int(tr[6, w, t]) - t0:6d}" for w in range(4)) + " | B " + " ".join(f"{int(tr[6, w, t]) - t0:6d}" for w in range(4, 8)))
+    pa = [int(tr[4, e, t]) - t0 for e in range(8)]
+    pb = [int(tr[5, e, t]) - t0 for e in range(8)]
+    print(f"        | last P arrival: leader A {int(tr[0, 6, t]) - t0:6d} B {int(tr[1, 6, t]) - t0:6d} | peer CTA: softA Srdy {pa[1]:6d} packed {pa[7]:6d} done {pa[5]:6d} last {pa[6]:6d}"
+          f" | softB Srdy {pb[1]:6d} packed {pb[7]:6d} done {pb[5]:6d} last {pb[6]:6d}")
 per = (int(tr[0, 1, 40]) - int(tr[0, 1, 8])) / 32
 print("cycles per KV iteration (2 Q tiles x 128 keys):", per, " -> MMA-ideal 2048")
 life = [int(tr[3, 7, i]) for i in range(5)]

@@ -108,6 +108,16 @@ __global__ void __launch_bounds__(384, 1) lab(int nwarps, int tiles, float scale
       const long long t0 = clock64();
       const int style = mma_mode >> 2;
       mma_mode &= 3;
+      if (mma_mode == 3) {
+        if (elect_one()) {
+          while (done_warps < nwarps) {
+            for (int i = 0; i < 64; ++i)
+              if (mbar_try_wait(smem_u32(&mbar), 0)) break;
+          }
+          out[148 * 8 * 5 + blockIdx.x * 2] = 1; out[148 * 8 * 5 + blockIdx.x * 2 + 1] = 1;
+        }
+        __syncwarp();
+      } else
       if (style == 1) {
         // one thread runs the whole issue loop (descriptors in its own registers), the other lanes wait at the end
         if (elect_one()) {
@@ -132,7 +142,6 @@ __global__ void __launch_bounds__(384, 1) lab(int nwarps, int tiles, float scale
           }
         }
         __syncwarp();
-        n_mma = __shfl_sync(0xffffffffu, (int)n_mma, 0) | 0ll;
         int mx = 0;
         for (int l = 0; l < 32; ++l) mx = max(mx, __shfl_sync(0xffffffffu, (int)n_mma, l));
         n_mma = mx;
@@ -343,11 +352,18 @@ static void run(const char* name, long long* d, float* sink, int mma_mode = 0) {
     const double k = 1.0 / ((double)n * tiles);
     printf("%-44s %d warp(s)/SMSP: %7.1f cycles/tile/warp (ld %6.1f max %6.1f exp %6.1f st %6.1f) -> SMSP period for 2 tiles %7.1f  %s\n", name,
            nw / 4, tot * k, ld * k, mx * k, ex * k, st * k, nw == 8 ? tot * k : 2 * tot * k, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    {
+      double per[4] = {0, 0, 0, 0};
+      for (int b = 0; b < 148; ++b)
+        for (int w = 0; w < nw; ++w) per[w & 3] += (double)h[((size_t)b * 8 + w) * 5] / (148.0 * (nw / 4) * tiles);
+      printf("      per scheduler (warp %% 4): %7.1f %7.1f %7.1f %7.1f\n", per[0], per[1], per[2], per[3]);
+    }
     if (mma_mode) printf("      with the MMA stream (%s): %.1f cycles / MMA\n", mma_mode == 1 ? "P from smem" : "P from TMEM", (double)h[148 * 8 * 5] / (double)h[148 * 8 * 5 + 1]);
   }
 }
 
 int main(int argc, char**) {
+  setvbuf(stdout, nullptr, _IOLBF, 0);
   long long* d; cudaMalloc(&d, 8 * (148 * 8 * 5 + 296)); float* sink; cudaMalloc(&sink, 4);
   const bool probes = argc > 1;
   if (probes) {
@@ -358,17 +374,10 @@ int main(int argc, char**) {
     run<0, 4>("v0 phases, EMU 4 (kernel today)", d, sink);
     run<2, 8>("v2 speculative max + chunked ld, EMU 8", d, sink);
   }
-  // what slows the MMA stream? (mode: 1 = P from smem, 2 = P from TMEM; +4 = one elected thread runs the whole issue loop)
-  for (int mm : {1, 5, 2, 6}) {
-    printf("---- MMA stream mode %d (%s, %s)\n", mm, (mm & 3) == 1 ? "PV operands both from smem" : "P from TMEM", (mm >> 2) ? "one thread issues" : "elect per MMA");
-    run<3, 9, false>("next to: idle warps", d, sink, mm);
-    run<3, 0, false>("next to: MUFU only", d, sink, mm);
-    run<3, 1, false>("next to: FFMA2 only", d, sink, mm);
-    run<3, 5, false>("next to: F2FP only", d, sink, mm);
-    run<3, 7, false>("next to: tcgen05.ld only", d, sink, mm);
-    run<3, 8, false>("next to: st.shared only", d, sink, mm);
-    run<0, 4, false>("next to: softmax v0 EMU 4", d, sink, mm);
-    run<2, 8, false>("next to: softmax v2 EMU 8", d, sink, mm);
+  // does the issuing warp (warp 9, scheduler 1) slow the softmax warps it shares a scheduler with?
+  for (int mm : {0, 3, 5, 6}) {
+    printf("---- warp 9: %s\n", mm == 0 ? "idle" : mm == 3 ? "one thread spinning on mbarrier.try_wait" : mm == 5 ? "one thread issuing MMAs flat out (SS PV), blocked on the full queue most of the time" : "one thread issuing MMAs flat out (TS PV)");
+    run<0, 4, false>("softmax v0 EMU 4", d, sink, mm);
   }
   return 0;
 }
