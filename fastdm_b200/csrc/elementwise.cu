@@ -1180,7 +1180,10 @@ __device__ __forceinline__ void quantize_vec_bf16(const U128& v, const QParams& 
 }
 
 // EXACT: the row is exactly VPT * 32 * WPR vectors wide (1536 / 3072 / 5120 columns are): no per-vector bounds checks
-template <int MODE /*0 fp8, 2 int8 asym, 3 none*/, bool ROUND_STEPS, int VPT, bool MODBF, int WPR /*warps per row*/, bool EXACT>
+// STAGE: one batch of modulation vectors. A and C are copied to shared memory once per CTA and the CTA walks over row groups
+// (grid = a few CTAs per SM): per-row re-reads of A and C from L2 were 2-4x the row's own bytes ([80640, 5120] with fp32
+// vectors: 3.2 GB of L2 reads next to 1.2 GB of HBM traffic)
+template <int MODE /*0 fp8, 2 int8 asym, 3 none*/, bool ROUND_STEPS, int VPT, bool MODBF, int WPR /*warps per row*/, bool EXACT, bool STAGE>
 __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 12 ? 2 : 1)))) ln_mod_quant_warp_kernel(
     const __nv_bfloat16* __restrict__ in, const void* __restrict__ A, const void* __restrict__ C,
     uint8_t* __restrict__ out, float* __restrict__ scale, int32_t* __restrict__ azp,
@@ -1188,13 +1191,27 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
     int64_t rows_per_batch, float eps) {
   using T = __nv_bfloat16;
   constexpr int LANES = 32 * WPR;   // lanes sharing a row
-  __shared__ float2 cells[3][8];
+  constexpr int MESZ = MODBF ? 2 : 4;
+  __shared__ float2 cells_all[6][8];
+  extern __shared__ __align__(16) uint8_t lnq_mods[];   // STAGE: A | C
   const int lane = threadIdx.x & (LANES - 1);
-  int64_t row = (int64_t)blockIdx.x * (256 / LANES) + (threadIdx.x / LANES);
+  if constexpr (STAGE) {
+    const int nbytes = cols * MESZ;
+    for (int i = threadIdx.x * 16; i < nbytes; i += 256 * 16) {
+      if (A) *reinterpret_cast<uint4*>(lnq_mods + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(A) + i));
+      if (C) *reinterpret_cast<uint4*>(lnq_mods + nbytes + i) = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(C) + i));
+    }
+    __syncthreads();
+  }
+  const int64_t n_groups = (rows + 256 / LANES - 1) / (256 / LANES);
+  int iter = 0;
+  for (int64_t grp = blockIdx.x; grp < n_groups; grp += gridDim.x, ++iter) {
+  float2 (*cells)[8] = cells_all + 3 * (iter & 1);   // (alternating cell sets: a warp may be one row ahead of its partner's reads)
+  int64_t row = grp * (256 / LANES) + (threadIdx.x / LANES);
   // (a pair past the last row keeps running on the last row so that it still meets its barriers; it writes nothing new)
   const bool live = row < rows;
   if (!live) {
-    if (WPR == 1) return;
+    if (WPR == 1) continue;
     row = rows - 1;
   }
   const int nvec = cols >> 3;
@@ -1259,8 +1276,14 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
         upk2(mul2f(add2f(pk2(bf16lo(w[q]), bf16hi(w[q])), nmean2), rstd2), n[2 * q], n[2 * q + 1]);
       if constexpr (MODBF) {
         // y = T(T(T(n) * A) + C) on packed bf16 pairs (A, C bf16): three native instructions per pair
-        const U128 a = A ? ldg128(reinterpret_cast<const T*>(A) + bidx * cols + v * 8) : U128{0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u};
-        const U128 c = C ? ldg128(reinterpret_cast<const T*>(C) + bidx * cols + v * 8) : U128{0u, 0u, 0u, 0u};
+        U128 a = U128{0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u}, c = U128{0u, 0u, 0u, 0u};
+        if constexpr (STAGE) {
+          if (A) { const uint4 t4 = *reinterpret_cast<const uint4*>(lnq_mods + v * 16); a = U128{t4.x, t4.y, t4.z, t4.w}; }
+          if (C) { const uint4 t4 = *reinterpret_cast<const uint4*>(lnq_mods + cols * MESZ + v * 16); c = U128{t4.x, t4.y, t4.z, t4.w}; }
+        } else {
+          if (A) a = ldg128(reinterpret_cast<const T*>(A) + bidx * cols + v * 8);
+          if (C) c = ldg128(reinterpret_cast<const T*>(C) + bidx * cols + v * 8);
+        }
         const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, cw[4] = {c.x, c.y, c.z, c.w};
         uint32_t y[4];
 #pragma unroll
@@ -1274,15 +1297,19 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
         }
         raw[i] = U128{y[0], y[1], y[2], y[3]};
       } else {
-        const float* Ar = A ? reinterpret_cast<const float*>(A) + bidx * cols + v * 8 : nullptr;
-        const float* Cr = C ? reinterpret_cast<const float*>(C) + bidx * cols + v * 8 : nullptr;
+        const float* Ar = A ? (STAGE ? reinterpret_cast<const float*>(lnq_mods) + v * 8 : reinterpret_cast<const float*>(A) + bidx * cols + v * 8) : nullptr;
+        const float* Cr = C ? (STAGE ? reinterpret_cast<const float*>(lnq_mods + cols * MESZ) + v * 8 : reinterpret_cast<const float*>(C) + bidx * cols + v * 8) : nullptr;
         float a[8], c[8];
         if (Ar) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(Ar)), a1 = __ldg(reinterpret_cast<const float4*>(Ar + 4));
+          float4 a0, a1;
+          if constexpr (STAGE) { a0 = *reinterpret_cast<const float4*>(Ar); a1 = *reinterpret_cast<const float4*>(Ar + 4); }
+          else { a0 = __ldg(reinterpret_cast<const float4*>(Ar)); a1 = __ldg(reinterpret_cast<const float4*>(Ar + 4)); }
           a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
         }
         if (Cr) {
-          const float4 c0 = __ldg(reinterpret_cast<const float4*>(Cr)), c1 = __ldg(reinterpret_cast<const float4*>(Cr + 4));
+          float4 c0, c1;
+          if constexpr (STAGE) { c0 = *reinterpret_cast<const float4*>(Cr); c1 = *reinterpret_cast<const float4*>(Cr + 4); }
+          else { c0 = __ldg(reinterpret_cast<const float4*>(Cr)); c1 = __ldg(reinterpret_cast<const float4*>(Cr + 4)); }
           c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
         }
         float f[8];
@@ -1315,11 +1342,11 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
       if (y_out && live) stg128(y_out + row * y_row_stride + (int64_t)v * 8, raw[i]);
     }
   }
-  if (MODE == 3) return;   // (no barrier follows)
+  if (MODE == 3) continue;   // (no barrier follows)
   mn = warp_min(fminf(bf16lo(mn2), bf16hi(mn2)));
   mx = warp_max(fmaxf(bf16lo(mx2), bf16hi(mx2)));
   group_exchange<WPR>(mn, mx, cells, 2, true);
-  if (!live) return;
+  if (!live) continue;
   const QParams p = make_qparams<MODE == 3 ? 0 : MODE>(mn, mx, fp8_amax_floor<T>());
   if (lane == 0) {
     scale[row] = p.scale;
@@ -1347,6 +1374,7 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
       }
     }
   }
+  }  // row groups
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1638,13 +1666,28 @@ static void launch_lnq_warp(const void* in, const void* A, const void* C, void* 
   // measured on [80640, 5120]: 2 warps per row 265 / 370 / 344 us (bf16 vectors / fp32 vectors / fp32 chain), 4 warps
   // 261 / 419 / 354 us, 1 warp (20 vectors per lane, 200 registers) 517 / 688 / 558 us
   int wpr = forced ? forced : (nvec <= 96 ? 1 : 2);
+  // one batch of modulation vectors that fits next to two CTAs' worth of shared memory: staged once per CTA, CTAs walk
+  // over the row groups (FDM_LNQ_STAGE=0 restores one CTA per row group reading A and C through L2)
+  static const int stage_on = [] { const char* e = getenv("FDM_LNQ_STAGE"); return e ? atoi(e) : 1; }();
+  const int mod_bytes = 2 * cols * (MODBF ? 2 : 4);
+  const bool stage = stage_on && (A || C) && rpb >= rows && mod_bytes <= 46 * 1024 && rows >= 2048;
 #define LNQW(V, W)                                                                                                      \
   do {                                                                                                                  \
-    if (nvec == V * 32 * W)                                                                                             \
-      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true><<<(unsigned)((rows + 8 / W - 1) / (8 / W)), 256, 0, st>>>(  \
+    const unsigned groups = (unsigned)((rows + 8 / W - 1) / (8 / W));                                                   \
+    if (stage) {                                                                                                        \
+      const unsigned per_sm = V <= 5 ? 4 : (V <= 6 ? 3 : (V <= 12 ? 2 : 1));                                            \
+      const unsigned g = groups < per_sm * (unsigned)num_sms() ? groups : per_sm * (unsigned)num_sms();                 \
+      if (nvec == V * 32 * W)                                                                                           \
+        ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true, true><<<g, 256, mod_bytes, st>>>(                         \
+            (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps); \
+      else                                                                                                              \
+        ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, false, true><<<g, 256, mod_bytes, st>>>(                        \
+            (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps); \
+    } else if (nvec == V * 32 * W)                                                                                      \
+      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true, false><<<groups, 256, 0, st>>>(                             \
           (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps);  \
     else                                                                                                                \
-      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, false><<<(unsigned)((rows + 8 / W - 1) / (8 / W)), 256, 0, st>>>( \
+      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, false, false><<<groups, 256, 0, st>>>(                            \
           (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps);  \
   } while (0)
   const int vpt = (nvec + 32 * wpr - 1) / (32 * wpr);

@@ -27,9 +27,11 @@ def sample(stop, out):
         time.sleep(0.05)
 
 
-for name, fn in (("fastdm_b200", lambda: ops.scaled_dot_product_attention(q, k, v, h, h, hd)),
-                 ("torch sdpa", lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4)),
-                 ("fastdm_b200 again", lambda: ops.scaled_dot_product_attention(q, k, v, h, h, hd))):
+runs = [("fastdm_b200", lambda: ops.scaled_dot_product_attention(q, k, v, h, h, hd))]
+if not os.environ.get("FDM_POWER_NO_TORCH"):
+    runs += [("torch sdpa", lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4)),
+             ("fastdm_b200 again", lambda: ops.scaled_dot_product_attention(q, k, v, h, h, hd))]
+for name, fn in runs:
     fn(); torch.cuda.synchronize()
     stop, out = threading.Event(), []
     th = threading.Thread(target=sample, args=(stop, out)); th.start()

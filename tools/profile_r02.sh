@@ -6,14 +6,14 @@ set -x
 O=gpurun_out
 NCU="ncu --clock-control none"
 B="--no-flux --no-sd3 --no-qwen --no-sparse --no-fp8-attention --no-torch-baseline --no-cpu-baseline --steps 1 --warmup 3"
-# Wan step: 760 launches per step; skip the 3 warm-up steps
-$NCU --metrics gpu__time_duration.sum -s 2280 -c 760 --csv --log-file $O/r02_wan_step_launches.csv python bench.py $B > $O/ncu_wan_stdout.log 2>&1
-# FLUX step, launched eagerly (the bench replays it as a CUDA graph): 627 launches per step
-$NCU --metrics gpu__time_duration.sum -s 1881 -c 627 --csv --log-file $O/r02_flux_step_launches.csv python bench.py --workload flux --no-graph $B > $O/ncu_flux_stdout.log 2>&1
-# top kernels, full metric set, raw pages only
-$NCU --set full -k regex:attn_fwd -s 2 -c 1 -o /tmp/p_attn_wan python tools/attn_one.py wan > $O/ncu_attn_wan.log 2>&1
+# one timed step each: bench.py brackets it with cudaProfilerStart/Stop when FDM_BENCH_PROFILE=1
+FDM_BENCH_PROFILE=1 $NCU --profile-from-start off --metrics gpu__time_duration.sum --csv --log-file $O/r02_wan_step_launches.csv python bench.py $B > $O/ncu_wan_stdout.log 2>&1
+# FLUX step, launched eagerly (the bench replays it as a CUDA graph)
+FDM_BENCH_PROFILE=1 $NCU --profile-from-start off --metrics gpu__time_duration.sum --csv --log-file $O/r02_flux_step_launches.csv python bench.py --workload flux --no-graph $B > $O/ncu_flux_stdout.log 2>&1
+# top kernels, full metric set, raw pages only (the tools launch each kernel twice: the second launch is captured)
+$NCU --set full --import-source on -k regex:attn_fwd -s 1 -c 1 -o /tmp/p_attn_wan python tools/attn_one.py wan > $O/ncu_attn_wan.log 2>&1
 ncu -i /tmp/p_attn_wan.ncu-rep --page raw --csv > $O/r02_attn_wan_raw.csv
-$NCU --set full -k regex:attn_fwd -s 2 -c 1 -o /tmp/p_attn_flux python tools/attn_one.py flux > $O/ncu_attn_flux.log 2>&1
+$NCU --set full --import-source on -k regex:attn_fwd -s 1 -c 1 -o /tmp/p_attn_flux python tools/attn_one.py flux > $O/ncu_attn_flux.log 2>&1
 ncu -i /tmp/p_attn_flux.ncu-rep --page raw --csv > $O/r02_attn_flux_raw.csv
 $NCU --set full -k regex:gemm_w8a8 -s 1 -c 1 -o /tmp/p_gemm python tools/gemm_one.py > $O/ncu_gemm.log 2>&1
 ncu -i /tmp/p_gemm.ncu-rep --page raw --csv > $O/r02_gemm_raw.csv
