@@ -1323,12 +1323,21 @@ __global__ void __launch_bounds__(256, (VPT <= 5 ? 4 : (VPT <= 6 ? 3 : (VPT <= 1
             upk2(t2, f[2 * q], f[2 * q + 1]);
           }
         } else {
+          // bf16 chain with fp32 vectors: T(T(T(n) * A) + C). The roundings go through the packed converter (two values per
+          // F2FP) instead of scalar cvt round trips, which run on the 16-lane XU pipe (ncu: XU 51 % busy with them)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = round_to<T>(n[j]);
-            if (Ar) t = round_to<T>(__fmul_rn(t, a[j]));
-            if (Cr) t = __fadd_rn(t, c[j]);
-            f[j] = t;
+          for (int q = 0; q < 4; ++q) {
+            uint32_t t2 = pack_bf16(n[2 * q], n[2 * q + 1]);
+            float t0 = bf16lo(t2), t1 = bf16hi(t2);
+            if (Ar) {
+              upk2(mul2f(pk2(t0, t1), pk2(a[2 * q], a[2 * q + 1])), t0, t1);
+              t2 = pack_bf16(t0, t1);
+              t0 = bf16lo(t2);
+              t1 = bf16hi(t2);
+            }
+            if (Cr) upk2(add2f(pk2(t0, t1), pk2(c[2 * q], c[2 * q + 1])), t0, t1);
+            f[2 * q] = t0;
+            f[2 * q + 1] = t1;
           }
         }
         raw[i] = pack8<T>(f);
