@@ -8,13 +8,17 @@
 //
 //   warps 0-3 : softmax + correction + epilogue of Q tile A (thread <-> query row)
 //   warps 4-7 : same for Q tile B
-//   warp  8   : TMA producer -- Q tiles once, then K(t), V(t), K(t+1), ... through an NS-stage ring
+//   warp  8   : TMA producer -- Q tiles once, then the K / V tiles through an NS-stage ring
 //               (128-byte swizzled [128 rows x 64 elements] boxes; OOB rows zero-filled)
-//   warp  9   : MMA issuer -- S_X = Q_X K^T (SS, K-major x K-major) into TMEM, then
-//               O_X += P_X V (TS: P read from TMEM where the softmax warps wrote it over S_X,
-//               V consumed MN-major straight from its row-major tile -- no transpose anywhere)
+//   warp  9   : MMA issuer (one elected thread runs the whole loop) -- S_X = Q_X K^T (SS, K-major x K-major) into TMEM,
+//               then O_X += P_X V with V consumed MN-major straight from its row-major tile (no transpose anywhere).
+//               Dense calls whose P does not alias S: warps 9, 10, 11 take turns group by group (see the issuer).
 //
 //   TMEM columns: S_A [0,128) | S_B [128,256) | O_A [256,256+HD) | O_B [384,384+HD)
+//   P_X: over S_X in TMEM (TS MMA; fp8, masked or short hd-128 calls), in the spare TMEM columns next to O_X (hd 64),
+//   or in shared memory (hd 128 CTA pairs: two CTAs of a cluster issue every MMA together as cta_group::2, M = 256).
+//   In the last two cases S_X is free as soon as the softmax warps hold it in registers and QK_X(t+1) goes out ahead
+//   of PV_X(t).
 //
 // Softmax is the usual online form in the exp2 domain with lazy rescaling: the running max only
 // moves (and O is only rescaled through TMEM) when it grows by more than 2^8, so the correction
