@@ -5,7 +5,9 @@ from fastdm_b200 import ops
 dev, bf = "cuda", torch.bfloat16
 g = torch.Generator(device=dev).manual_seed(0)
 # attention: CTA-pair path (hd 128, Sk >= 1024), legacy path (hd 64, short Sk, masked), fp8
-for (b, sq, sk, h, hd) in ((1, 700, 1100, 2, 128), (2, 300, 200, 2, 64), (1, 520, 512, 1, 128)):
+# attention: persistent CTA-pair kernel (hd 128, 9 KV tiles), one-item CTA-pair kernel with rotating issuers (18 tiles), hd 64 (dense: P next to
+# O in TMEM, rotating issuers), short Sk
+for (b, sq, sk, h, hd) in ((1, 700, 1100, 2, 128), (1, 700, 2200, 1, 128), (2, 300, 200, 2, 64), (1, 300, 2300, 1, 64), (1, 520, 512, 1, 128)):
     q = torch.randn(b, sq, h * hd, device=dev, generator=g).to(bf)
     k = torch.randn(b, sk, h * hd, device=dev, generator=g).to(bf)
     v = torch.randn(b, sk, h * hd, device=dev, generator=g).to(bf)
