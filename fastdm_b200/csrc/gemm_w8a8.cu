@@ -32,11 +32,16 @@ constexpr int kGemmThreads = 320; // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 constexpr int kGroupM = 16;       // m-tiles per rasterisation group (L2 reuse of B)
 
-template <int BN>
+// CG = 2: two CTAs of a cluster work on one 256-row tile as a pair (tcgen05.mma.cta_group::2, M = 256): each CTA stages
+// its own 128 rows of A and only HALF of the B tile (BN / 2 weight rows); the tensor cores exchange the halves. Per
+// k-block a CTA pulls 32 KB through L2 -> shared memory instead of 48 KB (128 x 256 tiles on every SM ask L2 for
+// ~94 B/clk/SM, ~26 TB/s chip-wide at full MMA rate: the single-CTA kernel is L2-bandwidth-bound at ~79 % tensor-pipe
+// activity), and the ring is 6 stages deep instead of 4.
+template <int BN, int CG = 1>
 struct GemmSmem {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = CG == 2 ? 6 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = kBM * kBK;
-  static constexpr int kBBytes = BN * kBK;
+  static constexpr int kBBytes = BN / CG * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kRing = kStages * kStageBytes;
   // epilogue per-column parameters: scale_b, bias, azp_adj, gate
@@ -46,6 +51,7 @@ struct GemmSmem {
   static constexpr int kBarBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kTotal = kBarOff + kBarBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN;                    // 512 / 256 / 128
+  static_assert(kTotal <= 232448, "gemm: shared-memory layout exceeds 227 KB");
 };
 
 struct GemmParams {
@@ -80,11 +86,16 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tn = r / gm;
 }
 
-template <bool INT8, int BN, int ACT>
+template <bool INT8, int BN, int ACT, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
+  static_assert(CG == 1 || BN == 256, "the CTA-pair variant is built for 256-column tiles");
+  // CTA pair: rank 0 (the leader) runs the MMA thread; the ring's full barriers and the accumulator-empty barriers live
+  // in the leader's shared memory, stage-empty and accumulator-full barriers are signalled in both CTAs (multicast commit)
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  constexpr int kTileM = kBM * CG;   // rows per tile of the pair
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;
@@ -115,35 +126,45 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 8);
+      mbar_init(tempty_bar(a), 8 * CG);   // one arrival per epilogue warp of every CTA of the pair
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<1>(smem_u32(tmem_ptr_smem), S::kTmemCols);
+  if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_ptr_smem), S::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();  // the peer's barriers are initialised before anything is signalled on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_tiles = p.tiles_m * p.tiles_n;
   const int num_kb = (p.K + kBK - 1) / kBK;
+  const int first_tile = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
         int tm, tn;
         tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
-        const int m0 = tm * kBM, n0 = tn * BN;
+        const int m0 = tm * kTileM + (int)rank * kBM, n0 = tn * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = base + stage * S::kStageBytes;
           const uint32_t sb = sa + S::kABytes;
-          mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m0);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n0);
+          if (CG == 2) {
+            // the leader's full barrier counts the bytes of both CTAs' boxes
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * S::kStageBytes);
+            const uint32_t full_lead = mapa_u32(full_bar(stage), 0);
+            tma_load_2d_cg2(sa, &tmap_a, full_lead, kb * kBK, m0);
+            tma_load_2d_cg2(sb, &tmap_b, full_lead, kb * kBK, n0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), S::kStageBytes);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * kBK, m0);
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * kBK, n0);
+          }
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -154,20 +175,22 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = first_tile; t < num_tiles; t += tile_step) {
         int tm, tn;
         tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
         const int n0 = tn * BN;
-        int n_eff = min(BN, p.N - n0);
+        // (a pair always multiplies the full BN columns: each CTA contributes exactly BN / 2 weight rows, rows beyond N
+        // are zero-filled by TMA and never stored)
+        int n_eff = CG == 2 ? BN : min(BN, p.N - n0);
         n_eff = (n_eff + 15) & ~15;
         const uint32_t idesc =
-            INT8 ? make_idesc(kFmtS8, kFmtS8, kAccS32, kBM, (uint32_t)n_eff)
-                 : make_idesc(kFmtE4M3, kFmtE4M3, kAccF32, kBM, (uint32_t)n_eff);
+            INT8 ? make_idesc(kFmtS8, kFmtS8, kAccS32, kTileM, (uint32_t)n_eff)
+                 : make_idesc(kFmtE4M3, kFmtE4M3, kAccF32, kTileM, (uint32_t)n_eff);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -180,16 +203,18 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advancing K inside the 128B swizzle row: +32 bytes -> +2 in the (>>4) address field
-            umma_ss<INT8 ? MmaKind::I8 : MmaKind::F8F6F4, 1>(d_tmem, adesc + 2u * k, bdesc + 2u * k,
-                                                              idesc, (uint32_t)((kb | k) != 0));
+            umma_ss<INT8 ? MmaKind::I8 : MmaKind::F8F6F4, CG>(d_tmem, adesc + 2u * k, bdesc + 2u * k,
+                                                               idesc, (uint32_t)((kb | k) != 0));
           }
-          tc_commit(empty_bar(stage));
+          if (CG == 2) tc_commit_cg2(empty_bar(stage), 0b11);  // the same stage in both CTAs
+          else tc_commit(empty_bar(stage));
           if (++stage == S::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(tfull_bar(acc));
+        if (CG == 2) tc_commit_cg2(tfull_bar(acc), 0b11);
+        else tc_commit(tfull_bar(acc));
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -204,10 +229,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     int tile_par = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, tile_par ^= 1) {
+    for (int t = first_tile; t < num_tiles; t += tile_step, tile_par ^= 1) {
       int tm, tn;
       tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
-      const int m0 = tm * kBM, n0 = tn * BN;
+      const int m0 = tm * kTileM + (int)rank * kBM, n0 = tn * BN;   // this CTA's 128 rows of the tile
       if (epi_tid == 0) s_gate_inexact[tile_par] = 0;  // last read two tiles ago
       named_bar_sync(1, kEpiThreads);
       for (int i = epi_tid; i < BN; i += kEpiThreads) {
@@ -422,7 +447,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) mbar_arrive_remote(tempty_bar(acc), 0);
+        else mbar_arrive(tempty_bar(acc));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -430,37 +458,51 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync();  // neither CTA's shared memory / TMEM goes away while the pair is still working
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<1>(tmem_base, S::kTmemCols);
+    tmem_dealloc<CG>(tmem_base, S::kTmemCols);
   }
 }
 
-template <bool INT8, int BN, int ACT>
+template <bool INT8, int BN, int ACT, int CG>
 static int launch_gemm_a(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                          cudaStream_t st) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   static std::atomic<bool> attr_set[64];  // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev].load(std::memory_order_acquire)) {
-    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN, ACT>,
+    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN, ACT, CG>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set[dev].store(true, std::memory_order_release);
   }
   const int tiles = p.tiles_m * p.tiles_n;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_w8a8_kernel<INT8, BN, ACT><<<grid, kGemmThreads, S::kTotal, st>>>(ta, tb, p);
+  const int slots = num_sms() / CG;   // CTAs, or CTA pairs
+  const int grid = (tiles < slots ? tiles : slots) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FDM_CUDA(cudaLaunchKernelEx(&cfg, gemm_w8a8_kernel<INT8, BN, ACT, CG>, ta, tb, p));
   FDM_LAUNCH_CHECK("gemm_w8a8 kernel launch");
   return FDM_OK;
 }
 
-template <bool INT8, int BN>
+template <bool INT8, int BN, int CG = 1>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                        cudaStream_t st) {
-  if (p.act == FDM_ACT_GELU_TANH) return launch_gemm_a<INT8, BN, FDM_ACT_GELU_TANH>(ta, tb, p, st);
-  if (p.act == FDM_ACT_GELU_ERF) return launch_gemm_a<INT8, BN, FDM_ACT_GELU_ERF>(ta, tb, p, st);
-  return launch_gemm_a<INT8, BN, FDM_ACT_NONE>(ta, tb, p, st);
+  if (p.act == FDM_ACT_GELU_TANH) return launch_gemm_a<INT8, BN, FDM_ACT_GELU_TANH, CG>(ta, tb, p, st);
+  if (p.act == FDM_ACT_GELU_ERF) return launch_gemm_a<INT8, BN, FDM_ACT_GELU_ERF, CG>(ta, tb, p, st);
+  return launch_gemm_a<INT8, BN, FDM_ACT_NONE, CG>(ta, tb, p, st);
 }
 
 static int gemm_common(bool int8, const void* a, const void* b, const float* scale_a,
@@ -499,7 +541,12 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
     if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
   }
   const int64_t tiles_n = (N + bn - 1) / bn;
-  FDM_REQUIRE(tiles_m * tiles_n < (1LL << 31), "gemm: too many tiles");
+  // CTA pairs (256 x 256 tiles) once there are enough of them to give every SM pair a tile
+  static const int pair_setting = [] { const char* e = getenv("FDM_GEMM_CG"); return e ? atoi(e) : 2; }();
+  const int64_t tiles_m2 = (M + 2 * kBM - 1) / (2 * kBM);
+  const bool pair = pair_setting == 2 && bn == 256 && tiles_m2 * tiles_n >= sms / 2;
+  const int64_t tiles_m_used = pair ? tiles_m2 : tiles_m;
+  FDM_REQUIRE(tiles_m_used * tiles_n < (1LL << 31), "gemm: too many tiles");
 
   CUtensorMap ta, tb;
   {
@@ -513,7 +560,7 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   {
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t strides[1] = {(uint64_t)ldb};
-    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)bn};
+    uint32_t box[2] = {(uint32_t)kBK, (uint32_t)(pair ? bn / 2 : bn)};   // a CTA of a pair stages half of the weight rows
     rc = make_tmap(&tb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, b, dims, strides, box,
                    CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -531,7 +578,7 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   p.ldd = ldd;
   p.out_dtype = out_dtype;
   p.act = act;
-  p.tiles_m = (int)tiles_m;
+  p.tiles_m = (int)tiles_m_used;
   p.tiles_n = (int)tiles_n;
   p.vec_store = (ldd % 8 == 0 && (uintptr_t)d % 16 == 0) ? 1 : 0;
   p.vec32 = (ldd % 16 == 0 && (uintptr_t)d % 32 == 0 &&
@@ -548,6 +595,7 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   p.round_steps = round_steps;
   cudaStream_t st = (cudaStream_t)stream;
+  if (pair) return int8 ? launch_gemm<true, 256, 2>(ta, tb, p, st) : launch_gemm<false, 256, 2>(ta, tb, p, st);
   if (int8) {
     if (bn == 256) return launch_gemm<true, 256>(ta, tb, p, st);
     if (bn == 128) return launch_gemm<true, 128>(ta, tb, p, st);
