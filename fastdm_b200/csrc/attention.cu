@@ -1258,6 +1258,14 @@ static int launch_attn_e(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   if constexpr (HD == 128 && DT != kDtE4M3) {
     if (attn_use_pair(p.Sq, p.Sk, p.mask != nullptr)) return launch_attn_p<HD, DT, EMU, true, 2>(tq, tk, tv, p, st, sp);
   }
+  if constexpr (DT == kDtE4M3) {
+    // fp8 operands: Q, K, V and P tiles are 16 KB, so a single CTA has room for P in shared memory next to a 6-stage ring
+    // (bf16 does not: 3 stages, which starve). S_X is then free as soon as the softmax warps hold it and QK_X(t+1) goes out
+    // ahead of PV_X(t), as in the CTA-pair kernel. Measured: 8704^2 x 24 heads 1288 -> 1621 TFLOP/s, 80640^2 x 4 heads
+    // 1847 -> 1784: dense calls of up to 16384 keys take it (FDM_ATTN_FP8_PS=0: never, =2: always)
+    static const int ps = attn_env("FDM_ATTN_FP8_PS", 1);
+    if (ps && p.mask == nullptr && sp == nullptr && p.Sk >= 4 * kKvTile && (ps == 2 || p.Sk <= 16384)) return launch_attn_p<HD, DT, EMU, true, 1>(tq, tk, tv, p, st, sp);
+  }
   return launch_attn_p<HD, DT, EMU, false, 1>(tq, tk, tv, p, st, sp);
 }
 
