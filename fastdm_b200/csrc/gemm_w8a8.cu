@@ -74,13 +74,14 @@ struct GemmParams {
   int64_t ldr;
   int64_t rows_per_batch;
   int round_steps;       // 1: T(gate * x) before the residual add (bf16 tensor-op chain)
+  int group_m;           // m-tiles per rasterisation group
 };
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
-  const int group_size = kGroupM * tiles_n;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  const int group_size = group_m * tiles_n;
   const int g = t / group_size;
-  const int first_m = g * kGroupM;
-  const int gm = min(kGroupM, tiles_m - first_m);
+  const int first_m = g * group_m;
+  const int gm = min(group_m, tiles_m - first_m);
   const int r = t - g * group_size;
   tm = first_m + r % gm;
   tn = r / gm;
@@ -148,7 +149,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         int tm, tn;
-        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
         const int m0 = tm * kTileM + (int)rank * kBM, n0 = tn * BN + (int)rank * (BN / CG);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -182,7 +183,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t acc_phase = 0;
       for (int t = first_tile; t < num_tiles; t += tile_step) {
         int tm, tn;
-        tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+        tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
         const int n0 = tn * BN;
         // (a pair always multiplies the full BN columns: each CTA contributes exactly BN / 2 weight rows, rows beyond N
         // are zero-filled by TMA and never stored)
@@ -231,7 +232,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int tile_par = 0;
     for (int t = first_tile; t < num_tiles; t += tile_step, tile_par ^= 1) {
       int tm, tn;
-      tile_coords(t, p.tiles_m, p.tiles_n, tm, tn);
+      tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, tm, tn);
       const int m0 = tm * kTileM + (int)rank * kBM, n0 = tn * BN;   // this CTA's 128 rows of the tile
       if (epi_tid == 0) s_gate_inexact[tile_par] = 0;  // last read two tiles ago
       named_bar_sync(1, kEpiThreads);
@@ -540,11 +541,14 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
     static const int forced_bn = [] { const char* e = getenv("FDM_GEMM_BN"); return e ? atoi(e) : 0; }();
     if (forced_bn == 64 || forced_bn == 128 || forced_bn == 256) bn = forced_bn;
   }
-  const int64_t tiles_n = (N + bn - 1) / bn;
   // CTA pairs (256 x 256 tiles) once there are enough of them to give every SM pair a tile
   static const int pair_setting = [] { const char* e = getenv("FDM_GEMM_CG"); return e ? atoi(e) : 2; }();
   const int64_t tiles_m2 = (M + 2 * kBM - 1) / (2 * kBM);
-  const bool pair = pair_setting == 2 && bn == 256 && tiles_m2 * tiles_n >= sms / 2;
+  // (measured: with fewer tiles than pair slots -- M = 512, N = 9216: 72 on 74 -- pairs are no faster than 128 x 128 tiles)
+  const int64_t tiles_n256 = (N + 255) / 256;
+  const bool pair = pair_setting == 2 && N > 128 && tiles_m2 * tiles_n256 >= sms / 2;
+  if (pair) bn = 256;
+  const int64_t tiles_n = (N + bn - 1) / bn;
   const int64_t tiles_m_used = pair ? tiles_m2 : tiles_m;
   FDM_REQUIRE(tiles_m_used * tiles_n < (1LL << 31), "gemm: too many tiles");
 
@@ -594,6 +598,10 @@ static int gemm_common(bool int8, const void* a, const void* b, const float* sca
   p.ldr = ldr;
   p.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1;
   p.round_steps = round_steps;
+  {
+    static const int forced_gm = [] { const char* e = getenv("FDM_GEMM_GROUP_M"); return e ? atoi(e) : 0; }();
+    p.group_m = forced_gm > 0 ? forced_gm : kGroupM;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (pair) return int8 ? launch_gemm<true, 256, 2>(ta, tb, p, st) : launch_gemm<false, 256, 2>(ta, tb, p, st);
   if (int8) {
