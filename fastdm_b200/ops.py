@@ -9,6 +9,7 @@ FastDM's kernel registry (see fastdm_b200/integration.py).
 """
 from typing import Optional, Tuple
 
+import contextlib
 import os
 
 import torch
@@ -59,8 +60,26 @@ def _cuda(t: torch.Tensor, what: str):
                            "(there is no CPU implementation)")
 
 
+# Host cost per call matters on the text streams and at 8-way sequence parallelism (a Qwen-Image step issues ~1100
+# launches of 5-40 us): `torch.cuda.current_stream(device).cuda_stream` and a `torch.cuda.device(...)` context were 13 of
+# the ~19 us a call took on the host (tools/host_overhead_profile.py); the raw-stream query and a guard that only
+# switches when the tensor lives on another device than the current one cost well under 1 us.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_cur_device = getattr(torch._C, "_cuda_getDevice", None)
+_NO_GUARD = contextlib.nullcontext()
+
+
 def _stream(t: torch.Tensor) -> int:
+    if _raw_stream is not None:
+        return _raw_stream(t.device.index)
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _on(t: torch.Tensor):
+    """Device guard for the launch: a no-op when `t` lives on the current device."""
+    if _cur_device is not None and t.device.index == _cur_device():
+        return _NO_GUARD
+    return torch.cuda.device(t.device)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -81,7 +100,7 @@ def _quant_fp8(x: torch.Tensor, act: int) -> Tuple[torch.Tensor, torch.Tensor]:
     out = torch.empty((rows, cols), device=x.device, dtype=torch.float8_e4m3fn)
     scale = torch.empty((rows, 1), device=x.device, dtype=torch.float32)
     lib = _lib.load()
-    with torch.cuda.device(x.device):
+    with _on(x):
         if act == ACT_NONE:
             rc = lib.fdm_quant_fp8(x.data_ptr(), out.data_ptr(), scale.data_ptr(), rows, cols,
                                    x.stride(0) if rows > 1 else cols, _dt(x, "quantize_to_fp8"), _stream(x))
@@ -111,7 +130,7 @@ def _quant_int8(x: torch.Tensor, symmetric: bool, act: int) -> Tuple[torch.Tenso
     azp = torch.empty((0 if symmetric else rows, 1), device=x.device, dtype=torch.int32)
     lib = _lib.load()
     stride = x.stride(0) if rows > 1 else cols
-    with torch.cuda.device(x.device):
+    with _on(x):
         if act == ACT_NONE:
             rc = lib.fdm_quant_int8(x.data_ptr(), out.data_ptr(), scale.data_ptr(),
                                     None if symmetric else azp.data_ptr(), rows, cols, stride,
@@ -146,7 +165,7 @@ def _rms_norm(x: torch.Tensor, weight: Optional[torch.Tensor], eps: float) -> to
     xc = x if x.is_contiguous() else x.contiguous()  # callers always pass contiguous (layer/transformer.py:275-290)
     out = torch.empty_like(xc)
     rows = xc.numel() // cols if cols else 0
-    with torch.cuda.device(x.device):
+    with _on(x):
         rc = _lib.load().fdm_rms_norm(xc.data_ptr(), out.data_ptr(), _ptr(weight), rows, cols, cols, cols,
                                       float(eps), _dt(x, "rms_norm"), _stream(x))
     _lib.check(rc, "rms_norm")
@@ -177,7 +196,7 @@ def _rope(query: torch.Tensor, key: torch.Tensor, head_size: int, cos_sin_cache:
     cs = cos_sin_cache
     if cs.dtype != query.dtype or cs.stride(1) != 1:
         cs = cs.to(query.dtype).contiguous()  # reference: cos/sin `.to(x.dtype)` (kernel/torch/rotemb.py:40-41)
-    with torch.cuda.device(query.device):
+    with _on(query):
         rc = _lib.load().fdm_rope(query.data_ptr(), key.data_ptr(), cs.data_ptr(), b, s, qd // head_size,
                                   kd // head_size, head_size, query.stride(0), query.stride(1),
                                   key.stride(0), key.stride(1), cs.stride(0), 1 if is_neox else 0,
@@ -194,7 +213,7 @@ def _gelu_and_mul(x: torch.Tensor) -> torch.Tensor:
     xc = x if x.is_contiguous() else x.contiguous()
     out = torch.empty(x.shape[:-1] + (d,), device=x.device, dtype=x.dtype)
     rows = xc.numel() // (2 * d) if d else 0
-    with torch.cuda.device(x.device):
+    with _on(x):
         rc = _lib.load().fdm_gelu_and_mul(xc.data_ptr(), out.data_ptr(), rows, d, 2 * d, d,
                                           _dt(x, "gelu_and_mul"), _stream(x))
     _lib.check(rc, "gelu_and_mul")
@@ -255,7 +274,7 @@ def _gemm_fp8(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, scale_a: torc
               residual: Optional[torch.Tensor], rows_per_batch: int, round_steps: bool) -> None:
     m, n, k = _check_mm(a, b, scale_a, scale_b, out.dtype, bias, "fp8_matmul", torch.float8_e4m3fn)
     _check_fused(out, m, n, out.dtype, gate, residual, rows_per_batch, "fp8_matmul")
-    with torch.cuda.device(a.device):
+    with _on(a):
         rc = _lib.load().fdm_gemm_fp8_residual(
             a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(), _ptr(bias), out.data_ptr(), m, n, k,
             a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k, out.stride(0) if m > 1 else n,
@@ -281,7 +300,7 @@ def _gemm_int8(out: torch.Tensor, a: torch.Tensor, b: torch.Tensor, scale_a: tor
             raise RuntimeError("fastdm_b200.int8_matmul: azp / azp_adj must be int32")
         if not (azp.is_contiguous() and azp_adj.is_contiguous()):
             raise RuntimeError("fastdm_b200.int8_matmul: azp / azp_adj must be contiguous")
-    with torch.cuda.device(a.device):
+    with _on(a):
         rc = _lib.load().fdm_gemm_int8_residual(
             a.data_ptr(), b.data_ptr(), scale_a.data_ptr(), scale_b.data_ptr(), _ptr(azp_adj), _ptr(azp), _ptr(bias),
             out.data_ptr(), m, n, k, a.stride(0) if m > 1 else k, b.stride(1) if n > 1 else k,
@@ -336,7 +355,7 @@ def _attn_fwd(out: torch.Tensor, query: torch.Tensor, key: torch.Tensor, value: 
             # trailing query / key blocks are computed
             block_mask = torch.nn.functional.pad(block_mask, (0, nbk - mk, 0, nbq - mq), value=1)
         block_mask = block_mask.contiguous()
-    with torch.cuda.device(query.device):
+    with _on(query):
         rc = _lib.load().fdm_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), _ptr(block_mask),
                                       b, sq, sk, num_heads, head_dim,
                                       q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1),
@@ -395,7 +414,7 @@ def attention_scatter(query, key, value, num_heads, head_dim, peer_ptrs, rows_pe
     arr = (ctypes.c_void_p * n)(*[int(p) for p in peer_ptrs])
     if scale is None:
         scale = head_dim ** -0.5
-    with torch.cuda.device(query.device):
+    with _on(query):
         rc = _lib.load().fdm_attn_fwd_scatter(q.data_ptr(), k.data_ptr(), v.data_ptr(), arr, n, int(rows_per_peer),
                                               _ptr(block_mask), sq, sk, num_heads, head_dim, q.stride(1), k.stride(1),
                                               v.stride(1), int(out_token_stride), mask_bq, mask_bk, float(scale),
@@ -428,7 +447,7 @@ def _qk_norm_rope(buf: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[to
             raise RuntimeError(f"fastdm_b200.{what}: cos_sin must be [>= pos0+tokens, head_size]")
         if cs.dtype != buf.dtype or cs.stride(1) != 1:
             cs = cs.to(buf.dtype).contiguous()
-    with torch.cuda.device(buf.device):
+    with _on(buf):
         rc = _lib.load().fdm_qk_norm_rope(buf.data_ptr(), _ptr(wq), _ptr(wk), _ptr(cs), tokens, q_heads, k_heads,
                                           head_size, buf.stride(0) if tokens > 1 else width, q_offset, k_offset, pos0,
                                           cs.stride(0) if cs is not None else 0, float(eps),
@@ -517,7 +536,7 @@ def ulysses_pack_heads(x: torch.Tensor, num_heads: int, head_dim: int, world: in
     if x.stride(1) != 1:
         x = x.contiguous()
     out = torch.empty((world, s, n_seg * c // world), device=x.device, dtype=x.dtype)
-    with torch.cuda.device(x.device):
+    with _on(x):
         rc = _lib.load().fdm_ulysses_pack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, head_dim, world, n_seg,
                                                 x.stride(0) if s > 1 else x.shape[1], c, x.element_size(), _stream(x))
     _lib.check(rc, "ulysses_pack_heads")
@@ -533,7 +552,7 @@ def ulysses_unpack_heads(x: torch.Tensor, num_heads: int, head_dim: int, n_seg: 
     x = x.contiguous()
     if out is None:
         out = torch.empty((s, n_seg * c), device=x.device, dtype=x.dtype)
-    with torch.cuda.device(x.device):
+    with _on(x):
         rc = _lib.load().fdm_ulysses_unpack_heads(x.data_ptr(), out.data_ptr(), s, num_heads, head_dim, world, n_seg,
                                                   out.stride(0) if s > 1 else out.shape[1], c, x.element_size(),
                                                   _stream(x))
@@ -552,7 +571,7 @@ def rel_l1_sums(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         raise RuntimeError("fastdm_b200.rel_l1_distance: a and b must have the same shape, dtype and device")
     a, b = a.contiguous(), b.contiguous()
     out = torch.empty(2, device=a.device, dtype=torch.float32)
-    with torch.cuda.device(a.device):
+    with _on(a):
         rc = _lib.load().fdm_rel_l1_distance(a.data_ptr(), b.data_ptr(), a.numel(), _dt(a, "rel_l1_distance"),
                                              out.data_ptr(), _stream(a))
     _lib.check(rc, "rel_l1_distance")
