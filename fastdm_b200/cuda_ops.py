@@ -14,8 +14,7 @@ from ._lib import FDM_BF16, FDM_E4M3, FDM_F16, FDM_F32
 _DT = {torch.bfloat16: FDM_BF16, torch.float16: FDM_F16, torch.float32: FDM_F32}
 
 
-def _stream(t):
-    return torch.cuda.current_stream(t.device).cuda_stream
+_stream, _on = ops._stream, ops._on   # raw current-stream query, device guard that is a no-op on the current device
 
 
 def fp8_quant_(out: torch.Tensor, input: torch.Tensor, scale: torch.Tensor, scale_ub: Optional[torch.Tensor] = None) -> None:
@@ -26,7 +25,7 @@ def fp8_quant_(out: torch.Tensor, input: torch.Tensor, scale: torch.Tensor, scal
         raise RuntimeError("fp8_quant_: input and out must be contiguous (elmwise_ops.cu:528-529)")
     cols = input.shape[-1]
     rows = input.numel() // cols
-    with torch.cuda.device(input.device):
+    with _on(input):
         rc = _lib.load().fdm_quant_fp8(input.data_ptr(), out.data_ptr(), scale.data_ptr(), rows, cols, cols,
                                        _DT[input.dtype], _stream(input))
     _lib.check(rc, "fp8_quant_")
@@ -38,7 +37,7 @@ def int8_quant_(out: torch.Tensor, input: torch.Tensor, scales: torch.Tensor, az
         raise RuntimeError("int8_quant_: input and out must be contiguous")
     cols = input.shape[-1]
     rows = input.numel() // cols
-    with torch.cuda.device(input.device):
+    with _on(input):
         rc = _lib.load().fdm_quant_int8(input.data_ptr(), out.data_ptr(), scales.data_ptr(),
                                         None if azp is None else azp.data_ptr(), rows, cols, cols,
                                         _DT[input.dtype], _stream(input))
@@ -49,7 +48,7 @@ def rms_norm_(out: torch.Tensor, input: torch.Tensor, weight: torch.Tensor, epsi
     """ops.h:15-18 / elmwise_ops.cu:433-449: normalises over input.size(-1) into the caller's out."""
     cols = input.shape[-1]
     rows = input.numel() // cols
-    with torch.cuda.device(input.device):
+    with _on(input):
         rc = _lib.load().fdm_rms_norm(input.data_ptr(), out.data_ptr(), None if weight is None else weight.data_ptr(),
                                       rows, cols, cols, cols, float(epsilon), _DT[input.dtype], _stream(input))
     _lib.check(rc, "rms_norm_")

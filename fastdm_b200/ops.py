@@ -493,7 +493,7 @@ def _ln_mod_quant(x: torch.Tensor, mul: Optional[torch.Tensor], add: Optional[to
     scale = torch.empty((rows if qdt is not None else 0, 1), device=dev, dtype=torch.float32)
     azp = torch.empty((rows if out_code == FDM_S8 else 0, 1), device=dev, dtype=torch.int32)
     y = torch.empty((rows, cols) if want_y else (0, cols), device=dev, dtype=x.dtype)
-    with torch.cuda.device(dev):
+    with _on(x):
         rc = _lib.load().fdm_layernorm_modulate_quant(
             x.data_ptr(), _ptr(mul), _ptr(add), q.data_ptr() if qdt is not None else None,
             scale.data_ptr() if qdt is not None else None, azp.data_ptr() if out_code == FDM_S8 else None,
