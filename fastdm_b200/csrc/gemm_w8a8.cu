@@ -87,7 +87,9 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   tn = r / gm;
 }
 
-template <bool INT8, int BN, int ACT, int CG>
+// GATED: the residual + gate * out epilogue is compiled in (its residual prefetch holds 64 registers; without it the
+// epilogue double-buffers its TMEM reads instead)
+template <bool INT8, int BN, int ACT, int CG, bool GATED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -250,7 +252,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (INT8) s_adj[i] = (ok && p.azp_adj != nullptr) ? p.azp_adj[col] : 0;
         // the gate row of the tile's batch, staged once per tile: read per element from global it was two thirds
         // of the epilogue's load instructions (ncu: 313 k load requests against 98 k stores, lg_throttle stalls)
-        if (p.gate != nullptr) {
+        if (GATED && p.gate != nullptr) {
           const float gv = ok ? p.gate[(int64_t)(m0 / p.rows_per_batch) * p.N + col] : 1.f;
           s_gate[i] = gv;
           s_gate16[i] = (uint16_t)(__float_as_uint(gv) >> 16);
@@ -269,8 +271,8 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // the residual rows do not depend on the accumulator: fetch this warp's share (BN/2 columns of its
       // row, 16-byte pieces) before waiting for the main loop, so their DRAM latency hides under it
       constexpr int kMyChunks = BN / 64;
-      U128 resv[kMyChunks][4];
-      if (p.residual != nullptr && row_ok) {
+      U128 resv[GATED ? kMyChunks : 1][4];
+      if (GATED && p.residual != nullptr && row_ok) {
         const uint16_t* rrow = reinterpret_cast<const uint16_t*>(p.residual) + (int64_t)row * p.ldr + n0;
 #pragma unroll
         for (int cc = 0; cc < kMyChunks; ++cc) {
@@ -289,13 +291,20 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)(acc * BN);
       const int n_valid = min(BN, p.N - n0);
+      // the TMEM read of chunk c+1 is in flight while chunk c is processed (two register buffers): with two epilogue
+      // warps per scheduler nothing else covers the tcgen05.ld latency (ncu: 25 % long-scoreboard stalls on it)
+      constexpr bool kPipe = !GATED;
+      uint32_t rbuf[kPipe ? 2 : 1][32];
+      if (kPipe && col_half * kMyChunks * 32 < n_valid) tmem_ld_32x32(t_row + (uint32_t)(col_half * kMyChunks * 32), rbuf[0]);
 #pragma unroll
       for (int cc = 0; cc < kMyChunks; ++cc) {
         const int c = col_half * kMyChunks + cc;
         if (c * 32 >= n_valid) break;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+        if (!kPipe) tmem_ld_32x32(t_row + (uint32_t)(c * 32), rbuf[0]);
         tmem_ld_wait();
+        if (kPipe && cc + 1 < kMyChunks && (c + 1) * 32 < n_valid)
+          tmem_ld_32x32(t_row + (uint32_t)((c + 1) * 32), rbuf[kPipe ? (cc + 1) & 1 : 0]);
+        uint32_t(&r)[32] = rbuf[kPipe ? cc & 1 : 0];
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -326,7 +335,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (row_ok) {
           const int col0 = n0 + c * 32;
           const bool bf = p.out_dtype == FDM_BF16;
-          if (p.gate != nullptr || p.residual != nullptr) {
+          if (GATED && (p.gate != nullptr || p.residual != nullptr)) {
             // reference chains (flux.py:153-154,161-163,69-72; wan.py:97,105,112): the linear's output
             // is a T tensor, then gate * out (+ rounding for bf16 tensor ops), then residual + .
             // rows of one tile normally share a batch (and with it the staged gate row)
@@ -466,15 +475,15 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <bool INT8, int BN, int ACT, int CG>
-static int launch_gemm_a(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+template <bool INT8, int BN, int ACT, int CG, bool GATED>
+static int launch_gemm_g(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                          cudaStream_t st) {
   using S = GemmSmem<BN, CG>;
   static std::atomic<bool> attr_set[64];  // zero-initialised; setting the attribute twice is harmless
   int dev = 0;
   FDM_CUDA(cudaGetDevice(&dev));
   if (!attr_set[dev].load(std::memory_order_acquire)) {
-    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN, ACT, CG>,
+    FDM_CUDA(cudaFuncSetAttribute(gemm_w8a8_kernel<INT8, BN, ACT, CG, GATED>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
     attr_set[dev].store(true, std::memory_order_release);
   }
@@ -493,9 +502,15 @@ static int launch_gemm_a(const CUtensorMap& ta, const CUtensorMap& tb, const Gem
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FDM_CUDA(cudaLaunchKernelEx(&cfg, gemm_w8a8_kernel<INT8, BN, ACT, CG>, ta, tb, p));
+  FDM_CUDA(cudaLaunchKernelEx(&cfg, gemm_w8a8_kernel<INT8, BN, ACT, CG, GATED>, ta, tb, p));
   FDM_LAUNCH_CHECK("gemm_w8a8 kernel launch");
   return FDM_OK;
+}
+
+template <bool INT8, int BN, int ACT, int CG>
+static int launch_gemm_a(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (p.gate != nullptr || p.residual != nullptr) return launch_gemm_g<INT8, BN, ACT, CG, true>(ta, tb, p, st);
+  return launch_gemm_g<INT8, BN, ACT, CG, false>(ta, tb, p, st);
 }
 
 template <bool INT8, int BN, int CG = 1>
