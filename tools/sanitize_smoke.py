@@ -28,6 +28,19 @@ ops.fp8_matmul(xq, wq.t(), xs, ws.view(-1), bf, bias, out=out, gate=gate, residu
 xi, si, zi = ops.quantize_to_int8(x, False); wi, wsi = ops.quantize_to_int8(w, True)[:2]
 adj = wi.to(torch.int32).sum(dim=1, dtype=torch.int32).view(1, -1).contiguous()
 ops.int8_matmul(xi, wi.t(), si, wsi.view(-1), bf, adj, zi, bias)
+# CTA-pair GEMM (>= 74 tiles of 256 x 256): plain, GELU, gated residual, int8 with zero points; ragged M (4870 rows)
+xl = torch.randn(4870, 256, device=dev, generator=g).to(bf); wl = (torch.randn(1024, 256, device=dev, generator=g) * 0.05).to(bf)
+xlq, xls = ops.quantize_to_fp8(xl); wlq, wls = ops.quantize_to_fp8(wl)
+bl = torch.randn(1024, device=dev).to(bf)
+yl = ops.fp8_matmul(xlq, wlq.t(), xls, wls.view(-1), bf, bl)
+ref = (xlq.float() * xls) @ (wlq.float() * wls).t() + bl.float()
+assert (yl.float() - ref).abs().max() <= 0.02 * ref.abs().max() + 0.05, "pair GEMM mismatch"
+ops.fp8_matmul(xlq, wlq.t(), xls, wls.view(-1), bf, bl, act="gelu_tanh")
+resl = torch.randn(4870, 1024, device=dev).to(bf); gl = torch.randn(1, 1024, device=dev).to(bf).float(); outl = torch.empty_like(resl)
+ops.fp8_matmul(xlq, wlq.t(), xls, wls.view(-1), bf, bl, out=outl, gate=gl, residual=resl, rows_per_batch=4870)
+xli, sli, zli = ops.quantize_to_int8(xl, False); wli, wlsi = ops.quantize_to_int8(wl, True)[:2]
+adjl = wli.to(torch.int32).sum(dim=1, dtype=torch.int32).view(1, -1).contiguous()
+ops.int8_matmul(xli, wli.t(), sli, wlsi.view(-1), bf, adjl, zli, bl)
 # elementwise
 ops.rms_norm(torch.randn(77, 4, 128, device=dev).to(bf), torch.randn(128, device=dev).to(bf), 1e-6)
 qq = torch.randn(1, 77, 4 * 128, device=dev).to(bf); kk = torch.randn(1, 77, 4 * 128, device=dev).to(bf)
