@@ -269,7 +269,10 @@ def test_matmul_golden(ops):
 # tests/test_matmul.py:5-44 (subset: every K, the ragged Ms, N=64, the K=15360 case)
 MM_SHAPES = [(4096, 3072, 9216), (512, 3072, 3072), (512, 12288, 3072), (4608, 15360, 3072), (14, 3072, 9216),
              (1178, 1536, 4608), (8192, 1536, 64), (2, 320, 1280), (154, 2048, 1280), (8192, 640, 1920),
-             (2048, 1280, 10240), (130, 144, 48)]
+             (2048, 1280, 10240), (130, 144, 48),
+             # CTA-pair GEMM (>= 74 tiles of 256 x 256) with a last row tile whose second CTA is entirely out of range,
+             # a ragged last column tile and a K that ends inside a 128-byte k-block
+             (1124, 272, 4624)]
 
 
 @pytest.mark.parametrize("shape", MM_SHAPES)
@@ -304,6 +307,24 @@ def test_matmul_int8_exact_accumulation(ops):
     y = ops.int8_matmul(a, b, one_m, one_n, BF, None, None, None)
     exact = (a.long().cpu() @ b.long().cpu())
     assert torch.equal(y.cpu(), exact.float().to(BF))
+
+
+def test_matmul_int8_exact_accumulation_cta_pairs(ops):
+    # the same exactness property on the CTA-pair kernel (81 tiles of 256 x 256), gated / residual epilogue included:
+    # residual + gate * T(acc) with unit gate and zero residual is still the bf16 rounding of the integer
+    g = torch.Generator(device=DEV).manual_seed(7)
+    M, K, N = 2304, 2048, 2304
+    a = torch.randint(-128, 128, (M, K), device=DEV, generator=g).to(torch.int8)
+    b = torch.randint(-128, 128, (N, K), device=DEV, generator=g).to(torch.int8).t()
+    one_m = torch.ones(M, 1, device=DEV)
+    one_n = torch.ones(N, 1, device=DEV)
+    y = ops.int8_matmul(a, b, one_m, one_n, BF, None, None, None)
+    exact = (a.float().cpu().double() @ b.float().cpu().double()).float().to(BF)   # |acc| < 2^26: exact in fp64
+    assert torch.equal(y.cpu(), exact)
+    out = torch.empty(M, N, device=DEV, dtype=BF)
+    ops.int8_matmul(a, b, one_m, one_n, BF, None, None, None, out=out, gate=torch.ones(1, N, device=DEV),
+                    residual=torch.zeros(M, N, device=DEV, dtype=BF), rows_per_batch=M)
+    assert torch.equal(out.cpu(), exact)
 
 
 def test_matmul_linearity_full_size(ops):
