@@ -1683,15 +1683,11 @@ static void launch_lnq_warp(const void* in, const void* A, const void* C, void* 
 #define LNQW(V, W)                                                                                                      \
   do {                                                                                                                  \
     const unsigned groups = (unsigned)((rows + 8 / W - 1) / (8 / W));                                                   \
-    if (stage) {                                                                                                        \
+    if (stage && nvec == V * 32 * W) { /* (staging is built for the exact widths only: 1536 / 3072 / 5120 columns are) */  \
       const unsigned per_sm = V <= 5 ? 4 : (V <= 6 ? 3 : (V <= 12 ? 2 : 1));                                            \
       const unsigned g = groups < per_sm * (unsigned)num_sms() ? groups : per_sm * (unsigned)num_sms();                 \
-      if (nvec == V * 32 * W)                                                                                           \
-        ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true, true><<<g, 256, mod_bytes, st>>>(                         \
-            (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps); \
-      else                                                                                                              \
-        ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, false, true><<<g, 256, mod_bytes, st>>>(                        \
-            (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps); \
+      ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true, true><<<g, 256, mod_bytes, st>>>(                           \
+          (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps);  \
     } else if (nvec == V * 32 * W)                                                                                      \
       ln_mod_quant_warp_kernel<MODE, RS, V, MODBF, W, true, false><<<groups, 256, 0, st>>>(                             \
           (const __nv_bfloat16*)in, A, C, (uint8_t*)out, scale, azp, (__nv_bfloat16*)y, rows, cols, is, ys, rpb, eps);  \
